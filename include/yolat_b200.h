@@ -1,0 +1,181 @@
+/*
+ * yolat_b200.h -- C ABI of the B200-native engine for YOLaT's Bezier-graph proposal classifier.
+ *
+ * The reference (microsoft/YOLaT-VectorGraphicsRecognition) has no FFI: its hot path is Python calling
+ * PyTorch / torch_scatter / PyG library kernels.  Each entry point below replaces one library-kernel
+ * chain at the call site cited next to it (paths relative to the reference tree).  All functions
+ *   - take plain device pointers + sizes (no torch types), fp32 values, int64 indices as delivered by
+ *     the reference Dataset, int32 internally;
+ *   - never allocate, never synchronise, never throw: outputs, tapes (activations saved for backward)
+ *     and workspaces are caller-allocated; sizes come from the *_floats / *_ints query functions;
+ *   - are stream-ordered on the `stream` argument (a cudaStream_t passed as void*), so they are safe
+ *     under CUDA-graph capture;
+ *   - return 0 on success or a negative yolat_status.
+ * Leading dimensions (ld*) are in elements and let a caller write into a column slice of a wider
+ * row-major matrix (this is how torch.cat at architecture3cc_rpn_gp_iter2.py:61,63,66,69,127 disappears).
+ */
+#ifndef YOLAT_B200_H_
+#define YOLAT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  YOLAT_OK = 0,
+  YOLAT_ERR_INVALID = -1,     /* bad argument (null pointer, unsupported channel count, ...) */
+  YOLAT_ERR_WORKSPACE = -2,   /* workspace / tape smaller than the *_floats query says        */
+  YOLAT_ERR_LAUNCH = -3,      /* a kernel launch failed (cudaGetLastError != cudaSuccess)      */
+  YOLAT_ERR_UNSUPPORTED = -4
+} yolat_status;
+
+int yolat_abi_version(void);
+const char* yolat_status_string(int status);
+/* last CUDA error string seen by a failing launch on this thread (diagnostics only) */
+const char* yolat_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph preparation.  Replaces what PyG's MessagePassing.propagate does implicitly on every call
+ * (gather by edge_index[0]/[1], scatter by edge_index[1]; gcn_lib/sparse/torch_vertex.py:324) with a
+ * once-per-batch CSR build shared by all conv layers and by backward.
+ *   edge: int64, element (e, c) at edge[e*stride_e + c*stride_c]; c=0 source j, c=1 target i.
+ *         ([E,2] contiguous: stride_e=2, stride_c=1; the transposed [2,E] view of
+ *          architecture3cc_rpn_gp_iter2.py:110 has stride_e=1... whatever strides torch reports.)
+ *   graph: int32 buffer of yolat_graph_ints(N,E) elements (layout private to the library).
+ * Out-of-range indices are counted in the buffer's error slot (read it with yolat_graph_errors after
+ * a sync) and the offending edges are dropped.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t yolat_graph_ints(int64_t N, int64_t E);
+int yolat_graph_build(const int64_t* edge, int64_t stride_e, int64_t stride_c, int64_t E, int64_t N,
+                      int32_t* graph, void* stream);
+/* device pointer to the int32 error counter inside a built graph buffer */
+const int32_t* yolat_graph_error_ptr(const int32_t* graph, int64_t N, int64_t E);
+/* device pointers to the CSR-by-target arrays (rowptr[N+1], src[E], eid[E]) for inspection/tests */
+const int32_t* yolat_graph_rowptr(const int32_t* graph, int64_t N, int64_t E);
+const int32_t* yolat_graph_src(const int32_t* graph, int64_t N, int64_t E);
+const int32_t* yolat_graph_eid(const int32_t* graph, int64_t N, int64_t E);
+
+/* Segments (proposals) from an index vector (bbox_idx).  Replaces the implicit grouping inside
+ * torch_scatter.scatter (architecture3cc_rpn_gp_iter2.py:67,122).  index need not be sorted.
+ *   seg: int32 buffer of yolat_segments_ints(M,S): segptr[S+1], perm[M] (rows of segment s are
+ *   perm[segptr[s] .. segptr[s+1]) in ascending row order). */
+int64_t yolat_segments_ints(int64_t M, int64_t S);
+int yolat_segments_build(const int64_t* index, int64_t M, int64_t S, int32_t* seg, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GraphConv('attr_edge_gp2')  ==  AttrRelativeEdgeConvGlobalPool2 (torch_vertex.py:288-341).
+ * Parameter block mirrors the module's state dict: nn.0 / nn.1 / nn.3 / nn.4 / lin_r / mlp_node.0 / .1
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* w;        /* gamma  [C] */
+  const float* b;        /* beta   [C] */
+  float* running_mean;   /* [C], updated in training mode (momentum 0.1) */
+  float* running_var;    /* [C], updated with the unbiased variance       */
+  int64_t* num_batches_tracked; /* may be NULL */
+} yolat_bn;
+
+typedef struct {
+  const float* w1; const float* b1; yolat_bn bn1;   /* nn.0 [C, 2Cin+4], nn.1 */
+  const float* w2; const float* b2; yolat_bn bn2;   /* nn.3 [C, C],      nn.4 */
+  const float* wr; const float* br;                 /* lin_r [C, Cin]         */
+  const float* wn; const float* bnode; yolat_bn bnn;/* mlp_node.0 [C, Cn], mlp_node.1 */
+} yolat_gp2_params;
+
+typedef struct {         /* gradient outputs, same shapes as the parameters; any pointer may be NULL */
+  float* w1; float* b1; float* bn1_w; float* bn1_b;
+  float* w2; float* b2; float* bn2_w; float* bn2_b;
+  float* wr; float* br;
+  float* wn; float* bnode; float* bnn_w; float* bnn_b;
+} yolat_gp2_grads;
+
+int64_t yolat_gp2_tape_floats(int64_t N, int64_t E, int Cin, int Cn, int C);
+int64_t yolat_gp2_fwd_ws_floats(int64_t N, int64_t E, int Cin, int Cn, int C);
+int64_t yolat_gp2_bwd_ws_floats(int64_t N, int64_t E, int Cin, int Cn, int C);
+
+/* forward (torch_vertex.py:319-337).  x [N,Cin], x_node [N,Cn], attr [E,4] in ORIGINAL edge order,
+ * edge_weight [E] or NULL (`norm`, :337).  out [N,C] = mean-aggregated messages + lin_r(x);
+ * xnode_out [N,C] = mlp_node(x_node).  training != 0: batch statistics + running-stat update. */
+int yolat_gp2_fwd(const yolat_gp2_params* p, int Cin, int Cn, int C,
+                  const float* x, int64_t ldx, const float* x_node, int64_t ldxn,
+                  const float* attr, const float* edge_weight,
+                  const int32_t* graph, int64_t N, int64_t E, int training,
+                  float* out, int64_t ldo, float* xnode_out, int64_t ldxo,
+                  float* tape, int64_t tape_floats, float* ws, int64_t ws_floats, void* stream);
+
+/* backward of the above.  g_out [N,C], g_xnode [N,C] (either may be NULL = zero).  dx [N,Cin] /
+ * dx_node [N,Cn] may be NULL (head layer: inputs are data).  accumulate_dx != 0 adds into dx / dx_node. */
+int yolat_gp2_bwd(const yolat_gp2_params* p, const yolat_gp2_grads* g, int Cin, int Cn, int C,
+                  const float* x, int64_t ldx, const float* x_node, int64_t ldxn,
+                  const float* attr, const float* edge_weight,
+                  const int32_t* graph, int64_t N, int64_t E, int training,
+                  const float* g_out, int64_t ldgo, const float* g_xnode, int64_t ldgx,
+                  float* dx, int64_t lddx, float* dx_node, int64_t lddxn, int accumulate_dx,
+                  const float* tape, float* ws, int64_t ws_floats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * One [Lin, BN?, ReLU?] stage of gcn_lib.sparse.MLP (torch_nn.py:50-71): y = act(bn(x W^T + b)).
+ * flags: bit0 = has BatchNorm, bit1 = has ReLU, bit2 = training.
+ * tape: z [M,Nout] (pre-BN) + 4*Nout statistics when BN is present.
+ * ---------------------------------------------------------------------------------------------- */
+#define YOLAT_MLP_BN 1
+#define YOLAT_MLP_RELU 2
+#define YOLAT_MLP_TRAINING 4
+int64_t yolat_mlp_tape_floats(int64_t M, int K, int Nout, int flags);
+int64_t yolat_mlp_ws_floats(int64_t M, int K, int Nout, int flags);
+int yolat_mlp_fwd(const float* x, int64_t ldx, int64_t M, int K, const float* w, const float* b, int Nout,
+                  const yolat_bn* bn, int flags, float* y, int64_t ldy,
+                  float* tape, int64_t tape_floats, float* ws, int64_t ws_floats, void* stream);
+int yolat_mlp_bwd(const float* x, int64_t ldx, int64_t M, int K, const float* w, int Nout,
+                  const yolat_bn* bn, int flags, const float* gy, int64_t ldgy,
+                  float* dx, int64_t lddx, int accumulate_dx, float* dw, float* db, float* dgamma, float* dbeta,
+                  const float* tape, float* ws, int64_t ws_floats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * torch_scatter.scatter(src, index, dim=0, reduce='mean'|'max')  (architecture3cc_rpn_gp_iter2.py:67,122)
+ * over prepared segments.  max: arg [S,C] int32 = row index of the maximum (first occurrence), -1 and
+ * value 0 for an empty segment; backward routes to that single row.
+ * ---------------------------------------------------------------------------------------------- */
+int yolat_segment_mean_fwd(const float* src, int64_t lds, int64_t M, int C, const int32_t* seg, int64_t S,
+                           float* out, int64_t ldo, void* stream);
+int yolat_segment_mean_bwd(const float* g, int64_t ldg, int64_t M, int C, const int32_t* seg, int64_t S,
+                           float* dsrc, int64_t ldd, int accumulate, void* stream);
+int yolat_segment_max_fwd(const float* src, int64_t lds, int64_t M, int C, const int32_t* seg, int64_t S,
+                          float* out, int64_t ldo, int32_t* arg, void* stream);
+int yolat_segment_max_bwd(const float* g, int64_t ldg, int64_t M, int C, int64_t S, const int32_t* arg,
+                          float* dsrc, int64_t ldd, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fusion_block + cat + scatter-max fused (architecture3cc_rpn_gp_iter2.py:62-63,122):
+ *   pooled[s, 0:F]   = max_{rows of s} relu(bn(feats W^T + b))      F = 1024
+ *   pooled[s, F:F+K] = max_{rows of s} feats                         K = fusion_dims
+ * without ever building out_feat [N, F+K].
+ * ---------------------------------------------------------------------------------------------- */
+int64_t yolat_fusemax_tape_floats(int64_t M, int K, int F, int64_t S);
+int64_t yolat_fusemax_ws_floats(int64_t M, int K, int F, int64_t S);
+int yolat_fusemax_fwd(const float* feats, int64_t ldf, int64_t M, int K, const float* w, const float* b, int F,
+                      const yolat_bn* bn, int training, const int32_t* seg, int64_t S,
+                      float* pooled, int64_t ldp, float* tape, int64_t tape_floats,
+                      float* ws, int64_t ws_floats, void* stream);
+int yolat_fusemax_bwd(const float* feats, int64_t ldf, int64_t M, int K, const float* w, int F,
+                      const yolat_bn* bn, int training, const int32_t* seg, int64_t S,
+                      const float* g_pooled, int64_t ldg,
+                      float* dfeats, int64_t lddf, int accumulate_dfeats,
+                      float* dw, float* db, float* dgamma, float* dbeta,
+                      float* tape, float* ws, int64_t ws_floats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CrossEntropyLoss(mean) (architecture3cc_rpn_gp_iter2.py:363,376).  prob [B,ncls] is the tape.
+ * bwd: dlogits = (softmax - onehot) * (*g_loss) / B, g_loss a DEVICE scalar (no host sync).
+ * Labels outside [0,ncls) contribute 0 and are counted in *bad_labels if non-NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int yolat_softmax_xent_fwd(const float* logits, int64_t ldl, int64_t B, int ncls, const int64_t* labels,
+                           float* loss, float* prob, float* ws, int64_t ws_floats, void* stream);
+int yolat_softmax_xent_bwd(const float* prob, int64_t B, int ncls, const int64_t* labels, const float* g_loss,
+                           float* dlogits, int64_t ldd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLAT_B200_H_ */

@@ -1,0 +1,3 @@
+class FlopCountAnalysis:
+    def __init__(self, *a, **k):
+        raise NotImplementedError

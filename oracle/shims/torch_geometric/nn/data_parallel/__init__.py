@@ -1,0 +1,3 @@
+class DataParallel:
+    def __init__(self, *a, **k):
+        raise NotImplementedError

@@ -1,0 +1,139 @@
+"""GPU parity of the whole hot path -- SparseCADGCN.forward + DetectionLoss + backward -- against the
+golden vectors of the UNMODIFIED reference (tests/golden/model_*.pt) and against the oracle restatement.
+
+Tolerances (measured noise floor of the reference against itself):
+  forward (logits, loss, BN running buffers): 1e-4 relative (max-abs / max|ref|) vs the fp64 reference;
+  end-to-end weight gradients: per-tensor L2 error vs the fp64 reference <= max(1e-4 * |g|, 2 x the
+  reference's own fp32-vs-fp64 error on that tensor) -- fp32 end-to-end gradients of this net are not
+  reproducible to 1e-4 by the reference itself (ReLU / arg-max flips);
+  biases that feed a training-mode BatchNorm: absolute (true value 0).
+"""
+import pytest
+import torch
+
+from util import load_golden, max_rel, sample, FWD_TOL
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    'toy': lambda s: s.toy_batch(),
+    'floorplans_small': lambda s: s.floorplans_batch(graphs=2, n=400, e=1600, seed=1),
+    'diagrams_small': lambda s: s.diagrams_batch(graphs=2, n=300, e=900, seed=2),
+    'floorplans_3blk': lambda s: s.floorplans_batch(graphs=1, n=320, e=1200, seed=3),
+}
+
+
+def _build(fx):
+    from types import SimpleNamespace
+    from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
+    opt = SimpleNamespace(**fx['opt'])
+    torch.manual_seed(fx['seed'])
+    model = arch.SparseCADGCN(opt)
+    return opt, model.cuda(), arch.DetectionLoss(opt)
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_model_step_matches_reference(name):
+    from yolat_vectorgraphicsrecognition_b200 import synth
+    fx = load_golden('model_%s.pt' % name)
+    opt, model, crit = _build(fx)
+    # identical seeded init as the reference
+    for k, v in model.state_dict().items():
+        assert abs(float(v.double().sum()) - fx['init_checksum'][k][0]) < 1e-9, k
+    batch = CASES[name](synth)
+    assert batch.x.shape[0] == fx['sizes']['N'] and batch.edge.shape[0] == fx['sizes']['E']
+    model.train()
+    out = model(batch, None)                      # CPU tensors in, like train.py:270
+    loss = crit(out, batch)['loss']
+    loss.backward()
+    assert out[0].shape == fx['logits64'].shape and torch.equal(out[1].cpu(), batch.bbox)
+    assert max_rel(out[0], fx['logits64']) < FWD_TOL, max_rel(out[0], fx['logits64'])
+    assert abs(float(loss) - fx['loss64']) < FWD_TOL * max(1.0, abs(fx['loss64']))
+    worst = {}
+    for k, p in model.named_parameters():
+        ref = fx['grad64_sample'][k]
+        got = sample(p.grad).double().cpu()
+        nrm, noise = fx['grad64_norm'][k], fx['grad32_noise'][k]
+        if fx['grad64_absmax'][k] < 1e-12:        # bias feeding a training-mode BN
+            assert float(p.grad.abs().max()) < 2e-5, k
+            continue
+        # errors are compared on the sub-sample, scaled to the full-tensor norm
+        scale = (p.grad.numel() / ref.numel()) ** 0.5
+        err = float((got - ref).norm()) * scale
+        bound = max(1e-4 * nrm, 2.0 * noise)
+        worst[k] = err / nrm
+        assert err <= bound * 1.5 + 1e-12, (k, err / nrm, bound / nrm)
+    sd = model.state_dict()
+    for k, v in fx['bn_after64'].items():
+        assert max_rel(sample(sd[k]), v) < FWD_TOL, k
+    for k, v in fx['bn_after'].items():
+        if 'num_batches' in k:
+            assert int(sd[k]) == int(v)
+    # eval mode with the updated running statistics
+    model.eval()
+    with torch.no_grad():
+        ev = model(batch, None)[0]
+    assert max_rel(ev, fx['eval_logits32']) < 5e-4      # fp32 reference of an fp32 chain of running-stat BNs
+
+
+def test_model_matches_oracle_config2_slice():
+    """One graph of config 2 (5k nodes / 20k edges) against the oracle restatement in fp64: forward 1e-4."""
+    from types import SimpleNamespace
+    from yolat_vectorgraphicsrecognition_b200 import synth
+    from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
+    from oracle import restatement as R
+    opt = synth.make_opt(n_classes=17)
+    torch.manual_seed(0)
+    model = arch.SparseCADGCN(opt)
+    st = R.clone_state(model.state_dict(), torch.float64)
+    batch = synth.floorplans_batch(graphs=1, seed=1)
+    ref = R.run_step(st, opt, batch, training=True)
+    model = model.cuda().train()
+    crit = arch.DetectionLoss(opt)
+    out = model(batch.to('cuda'), None)           # CUDA tensors in: .cuda() must be a no-op
+    loss = crit(out, batch)['loss']
+    loss.backward()
+    assert max_rel(out[0], ref['logits']) < FWD_TOL
+    assert abs(float(loss) - float(ref['loss'])) < FWD_TOL
+    for k, p in model.named_parameters():
+        g = ref['grads'][k]
+        if float(g.abs().max()) < 1e-12:
+            assert float(p.grad.abs().max()) < 2e-5, k
+        else:   # 5e-3: twice the reference's own fp32-vs-fp64 floor at this size
+            rel = float((p.grad.double().cpu() - g).norm() / g.norm())
+            assert rel < 5e-3, (k, rel)
+    for k, v in st.items():
+        if 'running' in k:
+            assert max_rel(model.state_dict()[k], v) < FWD_TOL, k
+
+
+def test_forward_is_deterministic():
+    """Segmented (atomic-free) reductions: two runs on the same input are bit-identical."""
+    from yolat_vectorgraphicsrecognition_b200 import synth
+    from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
+    opt = synth.make_opt(n_classes=17)
+    torch.manual_seed(0)
+    model = arch.SparseCADGCN(opt).cuda().eval()
+    batch = synth.floorplans_batch(graphs=1, n=800, e=3200, seed=4).to('cuda')
+    with torch.no_grad():
+        a = model(batch, None)[0]
+        b = model(batch, None)[0]
+    assert torch.equal(a, b)
+
+
+def test_unfused_backbone_signature():
+    """Backbone.forward keeps the reference signature and equals the fused pooled path after scatter-max."""
+    from yolat_vectorgraphicsrecognition_b200 import synth
+    from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
+    from yolat_vectorgraphicsrecognition_b200.torch_scatter import scatter
+    from yolat_vectorgraphicsrecognition_b200.graph import Segments
+    opt = synth.make_opt(n_classes=17)
+    torch.manual_seed(0)
+    model = arch.SparseCADGCN(opt).cuda().eval()
+    b = synth.floorplans_batch(graphs=1, n=640, e=2000, seed=6).to('cuda')
+    with torch.no_grad():
+        out_feat, out_super = model.cls_net(b.x, [b.edge.T], [None], [b.e_attr], b.bbox_idx)
+        assert out_feat.shape == (640, 1152) and out_super.shape == (40, 1152)
+        pooled, out_super2 = model.cls_net.forward_pooled(b.x, [b.edge.T], [None], [b.e_attr], Segments(b.bbox_idx, 40))
+        assert max_rel(scatter(out_feat, b.bbox_idx, dim=0, reduce='max'), pooled) < 1e-6
+        assert torch.equal(out_super, out_super2)

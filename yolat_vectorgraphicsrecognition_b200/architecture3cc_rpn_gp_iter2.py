@@ -1,0 +1,268 @@
+"""Drop-in for `cad_recognition/architecture3cc_rpn_gp_iter2.py`: `Backbone`, `SparseCADGCN`,
+`DetectionLoss` with the reference's constructor / forward / predict signatures, module attribute paths
+and state-dict keys, executing on the sm_100a kernels behind
+include/yolat_b200.h.  Reference line numbers below refer to that file.
+
+What changes under the same surface:
+  * the graph (CSR by target / by source) and the proposal segments are built once per forward and
+    shared by all conv layers and by backward;
+  * `fusion_block` -> `cat` -> `scatter(max)` (:62-63,122) is one fused op: out_feat [N,1152] is never built;
+  * there is no host synchronisation inside forward (the reference's scatter reads `index.max()`; the
+    number of proposals is taken from `data.bbox.shape[0]` instead).
+"""
+import numpy as np
+import torch
+from torch.nn import Linear as Lin
+
+from . import ops
+from .gcn_lib.sparse import MultiSeq, MLP, GraphConv, ResBlock
+from .graph import CSRGraph, Segments
+from .torch_scatter import scatter
+
+
+def _dev(t, device):
+    """`.cuda()` of the reference (:107-115), a no-op for tensors that already live on the device."""
+    return t if t.is_cuda else t.to(device, non_blocking=True)
+
+
+class Backbone(torch.nn.Module):
+    """:15-71"""
+
+    def __init__(self, opt, n_edges=3, edge_max_pool=torch.nn.AdaptiveAvgPool1d):
+        super(Backbone, self).__init__()
+        channels = opt.n_filters
+        act = opt.act
+        norm = opt.norm
+        bias = opt.bias
+        conv = 'attr_edge_gp2'  # opt.conv is ignored by the reference (:22)
+        c_growth = channels
+        n_edges = 1
+        self.n_edges = n_edges
+
+        self.n_blocks = opt.n_blocks
+        self.n_blocks_out = opt.n_blocks_out
+        self.heads = torch.nn.ModuleList()
+        self.n_classes = opt.n_classes
+        self.class_specific = opt.class_specific
+
+        self.head = GraphConv(opt.in_channels, channels, conv, act, norm, bias)
+        self.backbone = MultiSeq(*[ResBlock(channels, conv, act, norm, bias) for i in range(self.n_blocks - 1)])
+        fusion_dims = int(channels + c_growth * (self.n_blocks_out - 1))
+        self.fusion_block = MLP([fusion_dims, 1024], act, norm, bias)
+        self.fusion_block_super = MLP([fusion_dims, 1024], act, norm, bias)
+        self.fusion_dims = fusion_dims
+
+    # -- shared trunk: the conv stack (:45-57) and the feature-map selection (:60-61,65-66) -----------------
+    def _trunk(self, x, edges, edge_weights, edge_attrs):
+        graph = edges[0] if isinstance(edges[0], CSRGraph) else CSRGraph(edges[0], x.shape[0])
+        f, f_super = self.head(x, graph, edge_weights[0], edge_attrs[0], x_node=x)
+        feats, feats_super = [f], [f_super]
+        for i in range(self.n_blocks - 1):
+            f, f_super = self.backbone[i](feats[-1], graph, edge_weights[0], edge_attrs[0], x_node=feats_super[-1])
+            feats.append(f)
+            feats_super.append(f_super)
+        sel = range(self.n_blocks - self.n_blocks_out, self.n_blocks)
+        feats = torch.cat([feats[i] for i in sel], dim=1)
+        feats_super = torch.cat([feats_super[i] for i in sel], dim=1)
+        return feats, feats_super
+
+    def _super_branch(self, feats_super, seg):
+        feats_super = scatter(feats_super, seg, dim=0, reduce='mean')                   # :67
+        fusion_feats_super = self.fusion_block_super(feats_super)                        # :68
+        return torch.cat((fusion_feats_super, feats_super), dim=1)                       # :69
+
+    def forward(self, x, edges, edge_weights, edge_attrs, bbox_idx):
+        """Reference signature (:44); materialises out_feat [N, 1024 + fusion_dims] like the reference."""
+        feats, feats_super = self._trunk(x, edges, edge_weights, edge_attrs)
+        fusion_feats = self.fusion_block(feats)                                           # :62
+        out_feat = torch.cat((fusion_feats, feats), dim=1)                                # :63
+        seg = bbox_idx if isinstance(bbox_idx, Segments) else Segments(bbox_idx)
+        return out_feat, self._super_branch(feats_super, seg)
+
+    def forward_pooled(self, x, edges, edge_weights, edge_attrs, seg):
+        """Fused variant used by SparseCADGCN.forward: returns scatter(out_feat, 'max') [B, 1024 + fusion_dims]
+        (:62-63 + :122 in one op) and out_feat_super."""
+        feats, feats_super = self._trunk(x, edges, edge_weights, edge_attrs)
+        stages = self.fusion_block.stages()
+        if len(stages) == 1 and stages[0][0] == 'stage' and stages[0][2] is not None and stages[0][3]:
+            _, lin, bn, _ = stages[0]
+            pooled = ops.FuseMaxFn.apply(seg, bn.training, (bn.running_mean, bn.running_var, bn.num_batches_tracked),
+                                         feats, lin.weight, lin.bias, bn.weight, bn.bias)
+        else:   # non-default act / norm: unfused composition
+            pooled = scatter(torch.cat((self.fusion_block(feats), feats), dim=1), seg, dim=0, reduce='max')
+        return pooled, self._super_branch(feats_super, seg)
+
+
+class SparseCADGCN(torch.nn.Module):
+    """:73-356"""
+
+    def __init__(self, opt, n_edges=3, edge_max_pool=torch.nn.AdaptiveAvgPool1d, expand_ratio=0.25):
+        super(SparseCADGCN, self).__init__()
+        self.expand_ratio = expand_ratio
+        act = opt.act
+        norm = opt.norm
+        bias = opt.bias
+        self.n_classes = opt.n_classes
+        self.classifier = opt.classifier
+        self.class_specific = opt.class_specific
+        self.dim_stat = 0
+
+        self.cls_net = Backbone(opt)
+        self.prediction_cls = MultiSeq(*[
+            MLP([(self.cls_net.fusion_dims + 1024) * 2 + self.dim_stat, 512], act, norm, bias),
+            MLP([512, 256], act, norm, bias, drop=opt.dropout),
+            MLP([256, opt.n_classes], None, None, bias)])
+        self.model_init()
+
+    def model_init(self):
+        """:97-104 -- kaiming_normal_ on every Linear weight, zero biases (same module order => same RNG stream)."""
+        for m in self.modules():
+            if isinstance(m, Lin):
+                torch.nn.init.kaiming_normal_(m.weight)
+                m.weight.requires_grad = True
+                if m.bias is not None:
+                    m.bias.data.zero_()
+                    m.bias.requires_grad = True
+
+    def _device(self):
+        return next(self.parameters()).device
+
+    def forward(self, data, slices):
+        """:106-137.  `data` carries x [N,Cin], bbox_idx [N], edge [E,2], bbox [B,4], stat_feats, e_attr [E,4]
+        as CPU or CUDA tensors; returns (pred_cls [B,ncls], pred_bbox [B,4])."""
+        dev = self._device()
+        x = _dev(data.x, dev)
+        bbox_idx = _dev(data.bbox_idx, dev)
+        edge = _dev(data.edge, dev)
+        pred_bbox = _dev(data.bbox, dev)
+        e_attr = _dev(data.e_attr, dev)
+        # stat_feats is copied by the reference (:112) but unused (dim_stat = 0, :87): not moved here.
+
+        graph = CSRGraph(edge.T, x.shape[0])                   # edges = [data.edge.cuda().T]  (:110)
+        seg = Segments(bbox_idx, pred_bbox.shape[0])           # one proposal per bbox row: no index.max() sync
+        pooled, out_feat_cls_super = self.cls_net.forward_pooled(x, [graph], [None], [e_attr], seg)   # :121-122
+        out_feat_cls = torch.cat([pooled, out_feat_cls_super], dim=1)                                  # :127
+        pred_cls = self.prediction_cls(out_feat_cls)                                                   # :128
+        if self.classifier != 'softmax':
+            pred_cls = torch.sigmoid(pred_cls)                                                         # :132-133
+        return pred_cls, pred_bbox
+
+    # ----------------------------------------------------------------------------------------------
+    # two-stage inference (:139-356): classify the root proposal of every connected component, expand
+    # the children of the roots classified as background, classify those, interleave.
+    # ----------------------------------------------------------------------------------------------
+    @staticmethod
+    def _ranges(nodes, slices, key_lists):
+        """Concatenated index ranges for a list of (tree node, image index) pairs."""
+        out = {k: [] for k in ('pos', 'edge', 'edge_super')}
+        bbox = []
+        for node, i in nodes:
+            v = node.value
+            out['pos'].append(np.arange(v['idx_pos'][0], v['idx_pos'][1]) + int(slices['pos'][i]))
+            out['edge'].append(np.arange(v['idx_edge'][0], v['idx_edge'][1]) + int(slices['edge'][i]))
+            bbox.append(int(v['idx_bbox'] + slices['bbox'][i]))
+        cat = {k: (np.concatenate(v) if len(v) else np.zeros(0, dtype=np.int64)).astype(np.int64) for k, v in out.items()
+               if k != 'edge_super'}
+        return cat['pos'], cat['edge'], bbox
+
+    @staticmethod
+    def _build_data(data, slice_pos, slice_edge, slice_bbox):
+        """build_data (:167-234) without the per-edge / per-node python loops: old->new node renumbering is
+        a lookup table, the dense bbox_idx is a run-length cumsum."""
+        from types import SimpleNamespace
+        sp = torch.as_tensor(slice_pos, dtype=torch.long)
+        se = torch.as_tensor(slice_edge, dtype=torch.long)
+        x_all = data.x
+        o2n = torch.full((x_all.shape[0],), -1, dtype=torch.long)
+        o2n[sp] = torch.arange(sp.numel())
+        nd = SimpleNamespace()
+        nd.x = data.x.cpu()[sp] if not data.x.is_cuda else data.x[sp.to(data.x.device)]
+        nd.pos = data.pos[sp] if getattr(data, 'pos', None) is not None else None
+        old_bidx = data.bbox_idx.cpu()[sp]
+        nd.edge = o2n[data.edge.cpu()[se]]
+        nd.e_attr = data.e_attr.cpu()[se]
+        sb = torch.as_tensor(slice_bbox, dtype=torch.long)
+        nd.bbox = data.bbox.cpu()[sb]
+        nd.stat_feats = data.stat_feats.cpu()[sb] if getattr(data, 'stat_feats', None) is not None else None
+        if old_bidx.numel() > 0:
+            change = torch.zeros_like(old_bidx)
+            change[1:] = (old_bidx[1:] != old_bidx[:-1]).long()
+            nd.bbox_idx = torch.cumsum(change, 0)
+        else:
+            nd.bbox_idx = old_bidx
+        return nd
+
+    def predict(self, data, slices):
+        roots = data.roots
+        slice_root = slices['roots']
+        root_nodes, slice_image_bbox_root = [], [0]
+        for i in range(0, len(slice_root) - 1):
+            for root in roots[slice_root[i]:slice_root[i + 1]]:
+                root_nodes.append((root, i))
+            slice_image_bbox_root.append(len(root_nodes))
+        sp, se, slice_bbox = self._ranges(root_nodes, slices, None)
+        pred_cls, pred_bbox = self.forward(self._build_data(data, sp, se, slice_bbox), slices)
+
+        _, is_object = pred_cls.max(1)
+        has_object = (is_object == self.n_classes - 1).cpu()
+        slice_bbox_root = slice_bbox
+
+        child_nodes, slice_image_bbox_child = [], [0]
+        count = 0
+        for i in range(0, len(slice_root) - 1):
+            for root in roots[slice_root[i]:slice_root[i + 1]]:
+                if has_object[count]:
+                    for child in root.children:
+                        child_nodes.append((child, i))
+                count += 1
+            slice_image_bbox_child.append(len(child_nodes))
+        sp, se, slice_bbox = self._ranges(child_nodes, slices, None)
+
+        if len(sp) == 0:
+            slice_image_bbox = slice_image_bbox_root
+            slice_bbox = slice_bbox_root
+        else:
+            pred_cls2, pred_bbox2 = self.forward(self._build_data(data, sp, se, slice_bbox), slices)
+
+            def interleaf_pc(slice_p, slice_c, out_p, out_c):
+                out, s = [], [0]
+                for i in range(len(slice_c) - 1):
+                    out.append(out_p[slice_p[i]:slice_p[i + 1]])
+                    out.append(out_c[slice_c[i]:slice_c[i + 1]])
+                    s.append(s[-1] + slice_p[i + 1] - slice_p[i] + slice_c[i + 1] - slice_c[i])
+                return out, s
+
+            pred_cls, slice_image_bbox = interleaf_pc(slice_image_bbox_root, slice_image_bbox_child, pred_cls, pred_cls2)
+            pred_bbox, slice_image_bbox = interleaf_pc(slice_image_bbox_root, slice_image_bbox_child, pred_bbox,
+                                                       pred_bbox2)
+            slice_bbox, slice_image_bbox = interleaf_pc(slice_image_bbox_root, slice_image_bbox_child,
+                                                        torch.tensor(slice_bbox_root), torch.tensor(slice_bbox))
+            pred_cls = torch.cat(pred_cls, dim=0)
+            pred_bbox = torch.cat(pred_bbox, dim=0)
+            slice_bbox = torch.cat(slice_bbox, dim=0)
+
+        w = (pred_bbox[:, 2] - pred_bbox[:, 0]) * 1.05
+        h = (pred_bbox[:, 3] - pred_bbox[:, 1]) * 1.05
+        center_x = (pred_bbox[:, 2] + pred_bbox[:, 0]) / 2
+        center_y = (pred_bbox[:, 3] + pred_bbox[:, 1]) / 2
+        pred_bbox = torch.stack([center_x - w / 2, center_y - h / 2, center_x + w / 2, center_y + h / 2], dim=1)
+        return pred_cls, pred_bbox, None, slice_bbox, slice_image_bbox, None
+
+
+class DetectionLoss(torch.nn.Module):
+    """:358-379"""
+
+    def __init__(self, opt):
+        super(DetectionLoss, self).__init__()
+        self.classifier = opt.classifier
+        self.cls_loss = None if opt.classifier == 'softmax' else torch.nn.BCELoss()
+
+    def forward(self, out, data):
+        pred_cls = out[0]
+        gt_cls = _dev(data.labels, pred_cls.device)
+        if self.classifier == 'softmax':
+            l0 = ops.softmax_cross_entropy(pred_cls, gt_cls)      # CrossEntropyLoss(mean), :363,376
+        else:
+            gt = torch.zeros(pred_cls.size(), device=pred_cls.device).scatter_(1, gt_cls.unsqueeze(1), 1)
+            l0 = self.cls_loss(pred_cls, gt)
+        return {'loss': l0, 'loss_cls': l0}

@@ -1,0 +1,267 @@
+// bn.cu -- training/eval BatchNorm1d (+ReLU) forward statistics, apply, and backward over [M, C] row-major.
+//
+// Semantics: nn.BatchNorm1d(nc, affine=True) as built by gcn_lib/sparse/torch_nn.py:23-34 -- batch mean and
+// BIASED variance normalise in training mode, running buffers are updated with momentum 0.1 and the
+// UNBIASED variance; eval mode uses the running buffers.  Reductions are two-stage and deterministic:
+// fp32 partial sums per CTA (<= 128 addends per thread), combined in fp64.
+#include "common.cuh"
+
+namespace yolat {
+
+constexpr int ST_COLS = 32;   // columns per CTA (one warp-width => 128-byte coalesced row segments)
+constexpr int ST_ROWS = 8;    // row lanes per CTA
+constexpr int ST_ROWS_PER_CTA = 1024;
+
+// part layout: [nparts][2][C]
+__global__ void __launch_bounds__(ST_COLS* ST_ROWS) k_colstats(const float* __restrict__ z, int64_t ldz, int64_t M, int C,
+                                                                float* __restrict__ part) {
+  __shared__ float s1[ST_ROWS][ST_COLS], s2[ST_ROWS][ST_COLS];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * ST_COLS + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * ST_ROWS_PER_CTA;
+  const int64_t r1 = min(M, r0 + ST_ROWS_PER_CTA);
+  float a = 0.f, b = 0.f;
+  if (c < C) {
+    for (int64_t r = r0 + ty; r < r1; r += ST_ROWS) {
+      float v = z[r * ldz + c];
+      a += v;
+      b = fmaf(v, v, b);
+    }
+  }
+  s1[ty][tx] = a; s2[ty][tx] = b;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int q = 1; q < ST_ROWS; ++q) { a += s1[q][tx]; b += s2[q][tx]; }
+    part[((int64_t)blockIdx.y * 2 + 0) * C + c] = a;
+    part[((int64_t)blockIdx.y * 2 + 1) * C + c] = b;
+  }
+}
+
+__global__ void k_bn_finalize(const float* __restrict__ part, int nparts, int64_t M, int C, yolat_bn bn, int training,
+                              float* __restrict__ stat) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && bn.num_batches_tracked) *bn.num_batches_tracked += 1;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    double s = 0.0, ss = 0.0;
+    for (int p = 0; p < nparts; ++p) {
+      s += (double)part[((int64_t)p * 2 + 0) * C + c];
+      ss += (double)part[((int64_t)p * 2 + 1) * C + c];
+    }
+    const double mu = s / (double)M;
+    double v = ss / (double)M - mu * mu;
+    if (v < 0.0) v = 0.0;
+    mean = (float)mu;
+    var = (float)v;
+    if (bn.running_mean) bn.running_mean[c] = (1.f - kBnMomentum) * bn.running_mean[c] + kBnMomentum * mean;
+    if (bn.running_var) {
+      const double unbiased = M > 1 ? v * (double)M / (double)(M - 1) : v;
+      bn.running_var[c] = (1.f - kBnMomentum) * bn.running_var[c] + kBnMomentum * (float)unbiased;
+    }
+  } else {
+    mean = bn.running_mean[c];
+    var = bn.running_var[c];
+  }
+  const float invstd = 1.0f / sqrtf(var + kBnEps);
+  const float sc = bn.w[c] * invstd;
+  stat[c] = sc;
+  stat[C + c] = bn.b[c] - mean * sc;
+  stat[2 * C + c] = mean;
+  stat[3 * C + c] = invstd;
+}
+
+int bn_finalize_from_partials(const float* part, int nparts, int64_t M, int C, const yolat_bn* bn, int training,
+                              float* stat, cudaStream_t st) {
+  k_bn_finalize<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(part, nparts, M, C, *bn, training, stat);
+  YOLAT_CHECK_LAUNCH();
+  return YOLAT_OK;
+}
+
+int bn_forward_stats(const float* z, int64_t ldz, int64_t M, int C, const yolat_bn* bn, int training, float* stat,
+                     Arena& ws, cudaStream_t st) {
+  const int nparts = training ? (int)cdiv(M > 0 ? M : 1, ST_ROWS_PER_CTA) : 0;
+  float* part = training ? ws.take((int64_t)nparts * 2 * C) : nullptr;
+  if (ws.dry()) return YOLAT_OK;
+  if (ws.overflow) return YOLAT_ERR_WORKSPACE;
+  if (training) {
+    dim3 grid((unsigned)cdiv(C, ST_COLS), nparts);
+    k_colstats<<<grid, ST_COLS * ST_ROWS, 0, st>>>(z, ldz, M, C, part);
+    YOLAT_CHECK_LAUNCH();
+  }
+  return bn_finalize_from_partials(part, nparts, M, C, bn, training, stat, st);
+}
+
+// ---- apply -------------------------------------------------------------------------------------
+__global__ void k_bn_apply(const float* __restrict__ z, int64_t ldz, int64_t M, int C, const float* __restrict__ stat,
+                           int relu, float* __restrict__ y, int64_t ldy) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= M * C) return;
+  const int64_t r = idx / C;
+  const int c = (int)(idx % C);
+  float v = fmaf(z[r * ldz + c], stat[c], stat[C + c]);
+  if (relu) v = fmaxf(v, 0.f);
+  y[r * ldy + c] = v;
+}
+
+int bn_apply(const float* z, int64_t ldz, int64_t M, int C, const float* stat, int relu, float* y, int64_t ldy,
+             cudaStream_t st) {
+  if (M * C <= 0) return YOLAT_OK;
+  k_bn_apply<<<(unsigned)cdiv(M * C, 256), 256, 0, st>>>(z, ldz, M, C, stat, relu, y, ldy);
+  YOLAT_CHECK_LAUNCH();
+  return YOLAT_OK;
+}
+
+// ---- backward ----------------------------------------------------------------------------------
+__device__ __forceinline__ float bwd_load_dy(const BnBwdArgs& a, int64_t r, int c) {
+  int64_t row = a.row_idx ? (int64_t)a.row_idx[r] : r;
+  float v = a.gy[row * a.ldgy + c];
+  if (a.row_scale) v *= a.row_scale[row];
+  if (a.slot_scale) v *= a.slot_scale[a.slot_idx ? a.slot_idx[r] : r];
+  return v;
+}
+
+// partial sums of dy' and dy'*xhat per column.  part: [nparts][2][C]
+__global__ void __launch_bounds__(ST_COLS* ST_ROWS) k_bn_bwd_partial(BnBwdArgs a, float* __restrict__ part) {
+  __shared__ float s1[ST_ROWS][ST_COLS], s2[ST_ROWS][ST_COLS];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * ST_COLS + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * ST_ROWS_PER_CTA;
+  const int64_t r1 = min(a.M, r0 + ST_ROWS_PER_CTA);
+  float p = 0.f, q = 0.f;
+  if (c < a.C) {
+    const float sc = a.stat[c], sh = a.stat[a.C + c], mean = a.stat[2 * a.C + c], invstd = a.stat[3 * a.C + c];
+    for (int64_t r = r0 + ty; r < r1; r += ST_ROWS) {
+      const float zz = a.z[r * a.ldz + c];
+      float dy = bwd_load_dy(a, r, c);
+      if (a.relu && !(fmaf(zz, sc, sh) > 0.f)) dy = 0.f;
+      p += dy;
+      q = fmaf(dy, (zz - mean) * invstd, q);
+    }
+  }
+  s1[ty][tx] = p; s2[ty][tx] = q;
+  __syncthreads();
+  if (ty == 0 && c < a.C) {
+#pragma unroll
+    for (int k = 1; k < ST_ROWS; ++k) { p += s1[k][tx]; q += s2[k][tx]; }
+    part[((int64_t)blockIdx.y * 2 + 0) * a.C + c] = p;
+    part[((int64_t)blockIdx.y * 2 + 1) * a.C + c] = q;
+  }
+}
+
+// bstat: [0] m1 = sum(dy')/M, [1] m2 = sum(dy'*xhat)/M  (both 0 in eval mode: statistics are constants)
+__global__ void k_bn_bwd_finalize(const float* __restrict__ part, int nparts, int64_t M, int C,
+                                  const float* __restrict__ stat, const float* __restrict__ gamma, int training,
+                                  float* __restrict__ bstat, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                  float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, t = 0.0;
+  for (int p = 0; p < nparts; ++p) {
+    s += (double)part[((int64_t)p * 2 + 0) * C + c];
+    t += (double)part[((int64_t)p * 2 + 1) * C + c];
+  }
+  if (dgamma) dgamma[c] = (float)t;
+  if (dbeta) dbeta[c] = (float)s;
+  if (training) {
+    bstat[c] = (float)(s / (double)M);
+    bstat[C + c] = (float)(t / (double)M);
+    // sum_m dz[m,c] = gamma*invstd*(S - M*m1 - m2*sum(xhat)) == 0 exactly: a bias feeding a training-mode BN
+    if (dbias) dbias[c] = 0.f;
+  } else {
+    bstat[c] = 0.f;
+    bstat[C + c] = 0.f;
+    if (dbias) dbias[c] = (float)(s * (double)stat[c]);   // dz = dy' * sc
+  }
+}
+
+__global__ void k_bn_bwd_apply(BnBwdArgs a, const float* __restrict__ bstat) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= a.M * a.C) return;
+  const int64_t r = idx / a.C;
+  const int c = (int)(idx % a.C);
+  const float sc = a.stat[c], sh = a.stat[a.C + c], mean = a.stat[2 * a.C + c], invstd = a.stat[3 * a.C + c];
+  const float zz = a.z[r * a.ldz + c];
+  float dy = bwd_load_dy(a, r, c);
+  if (a.relu && !(fmaf(zz, sc, sh) > 0.f)) dy = 0.f;
+  const float xhat = (zz - mean) * invstd;
+  a.dz[r * a.lddz + c] = sc * (dy - bstat[c] - xhat * bstat[a.C + c]);
+}
+
+int bn_bwd_finalize(const float* part, int nparts, int64_t M, int C, const float* stat, const float* gamma, int training,
+                    float* bstat, float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
+  k_bn_bwd_finalize<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(part, nparts, M, C, stat, gamma, training, bstat, dgamma,
+                                                            dbeta, dbias);
+  YOLAT_CHECK_LAUNCH();
+  return YOLAT_OK;
+}
+
+int bn_backward(const BnBwdArgs& a, Arena& ws, cudaStream_t st) {
+  const int nparts = (int)cdiv(a.M > 0 ? a.M : 1, ST_ROWS_PER_CTA);
+  float* part = ws.take((int64_t)nparts * 2 * a.C);
+  float* bstat = ws.take(2 * a.C);
+  if (ws.dry()) return YOLAT_OK;
+  if (ws.overflow) return YOLAT_ERR_WORKSPACE;
+  dim3 grid((unsigned)cdiv(a.C, ST_COLS), nparts);
+  k_bn_bwd_partial<<<grid, ST_COLS * ST_ROWS, 0, st>>>(a, part);
+  YOLAT_CHECK_LAUNCH();
+  YOLAT_TRY(bn_bwd_finalize(part, nparts, a.M, a.C, a.stat, a.gamma, a.training, bstat, a.dgamma, a.dbeta, a.dbias, st));
+  if (a.M * a.C > 0 && a.dz) {
+    k_bn_bwd_apply<<<(unsigned)cdiv(a.M * a.C, 256), 256, 0, st>>>(a, bstat);
+    YOLAT_CHECK_LAUNCH();
+  }
+  return YOLAT_OK;
+}
+
+// ---- misc --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ST_COLS* ST_ROWS) k_colsum_partial(const float* __restrict__ z, int64_t ldz, int64_t M,
+                                                                      int C, float* __restrict__ part) {
+  __shared__ float s1[ST_ROWS][ST_COLS];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * ST_COLS + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * ST_ROWS_PER_CTA;
+  const int64_t r1 = min(M, r0 + ST_ROWS_PER_CTA);
+  float a = 0.f;
+  if (c < C)
+    for (int64_t r = r0 + ty; r < r1; r += ST_ROWS) a += z[r * ldz + c];
+  s1[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int q = 1; q < ST_ROWS; ++q) a += s1[q][tx];
+    part[(int64_t)blockIdx.y * C + c] = a;
+  }
+}
+__global__ void k_colsum_final(const float* __restrict__ part, int nparts, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += (double)part[(int64_t)p * C + c];
+  out[c] = (float)s;
+}
+
+int colsum(const float* a, int64_t lda, int64_t M, int C, float* out, Arena& ws, cudaStream_t st) {
+  const int nparts = (int)cdiv(M > 0 ? M : 1, ST_ROWS_PER_CTA);
+  float* part = ws.take((int64_t)nparts * C);
+  if (ws.dry()) return YOLAT_OK;
+  if (ws.overflow) return YOLAT_ERR_WORKSPACE;
+  dim3 grid((unsigned)cdiv(C, ST_COLS), nparts);
+  k_colsum_partial<<<grid, ST_COLS * ST_ROWS, 0, st>>>(a, lda, M, C, part);
+  YOLAT_CHECK_LAUNCH();
+  k_colsum_final<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(part, nparts, C, out);
+  YOLAT_CHECK_LAUNCH();
+  return YOLAT_OK;
+}
+
+__global__ void k_fill_zero(float* __restrict__ p, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+int fill_zero(float* p, int64_t n, cudaStream_t st) {
+  if (n <= 0) return YOLAT_OK;
+  cudaMemsetAsync(p, 0, n * sizeof(float), st);
+  return YOLAT_OK;
+}
+
+}  // namespace yolat

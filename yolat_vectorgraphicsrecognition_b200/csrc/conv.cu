@@ -1,0 +1,273 @@
+// conv.cu -- GraphConv('attr_edge_gp2') forward / backward: the C-ABI entry points and their kernel schedule.
+//
+// Reference: AttrRelativeEdgeConvGlobalPool2, gcn_lib/sparse/torch_vertex.py:288-341 (forward :319-328,
+// message :330-337, aggr='mean' :308), built on gcn_lib.sparse.MLP (torch_nn.py:50-71).
+//
+// Schedule (training forward):
+//   Wpq  = [W1a - W1b ; W1b]                      k_prep_wpq
+//   PQ   = x Wpq^T                    [N,2C]      GEMM (node-level; replaces the edge-level Lin1)
+//   z1   = P[i] + Q[j] + W1c attr + b1 [E,C]      k_edge_z1  (+ BN1 partial sums)   CSR-by-target slot order
+//   z2   = relu(bn1(z1)) W2^T + b2     [E,C]      GEMM with BN+ReLU operand prologue
+//   out  = x Wr^T + br                 [N,C]      GEMM
+//   out += mean_i relu(bn2(z2))                   k_edge_agg (segmented, no atomics)
+//   xn   = relu(bn_n(x_node Wn^T + bn))           GEMM + column stats + apply
+// Tape (saved for backward): z1, z2, zn and the three BN statistic blocks.
+#include "common.cuh"
+
+namespace yolat {
+
+struct Gp2Tape {
+  float* z1; float* z2; float* zn; float* stat1; float* stat2; float* statn;
+};
+
+static void gp2_tape_layout(Arena& t, int64_t N, int64_t E, int C, Gp2Tape* o) {
+  o->z1 = t.take(E * C);
+  o->z2 = t.take(E * C);
+  o->zn = t.take(N * C);
+  o->stat1 = t.take(4 * C);
+  o->stat2 = t.take(4 * C);
+  o->statn = t.take(4 * C);
+}
+
+static bool gp2_channels_ok(int Cin, int Cn, int C) {
+  return (C == 32 || C == 64 || C == 128) && Cin >= 1 && Cn >= 1;
+}
+
+static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const float* x, int64_t ldx,
+                        const float* x_node, int64_t ldxn, const float* attr, const float* ew,
+                        const int32_t* graph, int64_t N, int64_t E, int training, float* out, int64_t ldo,
+                        float* xnode_out, int64_t ldxo, Arena& tape, Arena& ws, cudaStream_t st) {
+  const bool dry = ws.dry();
+  Gp2Tape t;
+  gp2_tape_layout(tape, N, E, C, &t);
+  float* wpq = ws.take((int64_t)2 * C * Cin);
+  float* pq = ws.take(N * 2 * C);
+  const int nparts = edge_z1_nparts(N);
+  float* part1 = ws.take((int64_t)nparts * 2 * C);
+  if (!dry && (ws.overflow || tape.overflow)) return YOLAT_ERR_WORKSPACE;
+
+  GraphView g;
+  if (!dry) graph_layout(N, E, graph, &g);
+
+  // ---- lin_r: out = x Wr^T + br  (torch_vertex.py:325) ------------------------------------------
+  {
+    GemmArgs a{};
+    a.A = x; a.lda = ldx; a.B = dry ? nullptr : p->wr; a.ldb = Cin; a.C = out; a.ldc = ldo;
+    a.M = (int)N; a.N = C; a.K = Cin; a.bias = dry ? nullptr : p->br;
+    YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
+  }
+  // ---- edge path ---------------------------------------------------------------------------------
+  if (E > 0) {
+    if (!dry) YOLAT_TRY(edge_prep_wpq(p->w1, Cin, C, wpq, st));
+    {
+      GemmArgs a{};
+      a.A = x; a.lda = ldx; a.B = wpq; a.ldb = Cin; a.C = pq; a.ldc = 2 * C;
+      a.M = (int)N; a.N = 2 * C; a.K = Cin;
+      YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
+    }
+    if (!dry) {
+      YOLAT_TRY(edge_z1(g, N, C, pq, attr, p->w1, Cin, p->b1, t.z1, training ? part1 : nullptr, st));
+      YOLAT_TRY(bn_finalize_from_partials(part1, nparts, E, C, &p->bn1, training, t.stat1, st));
+    }
+    {
+      GemmArgs a{};
+      a.A = t.z1; a.lda = C; a.B = dry ? nullptr : p->w2; a.ldb = C; a.C = t.z2; a.ldc = C;
+      a.M = (int)E; a.N = C; a.K = C; a.bias = dry ? nullptr : p->b2;
+      a.a_sc = t.stat1; a.a_sh = dry ? nullptr : t.stat1 + C;
+      YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
+    }
+    yolat_bn bn2 = dry ? yolat_bn{} : p->bn2;
+    YOLAT_TRY(bn_forward_stats(t.z2, C, E, C, &bn2, training, t.stat2, ws, st));
+    if (!dry) YOLAT_TRY(edge_agg(g, N, C, t.z2, t.stat2, ew, out, ldo, st));
+  }
+  // ---- node path: mlp_node(x_node)  (torch_vertex.py:326) -----------------------------------------
+  {
+    GemmArgs a{};
+    a.A = x_node; a.lda = ldxn; a.B = dry ? nullptr : p->wn; a.ldb = Cn; a.C = t.zn; a.ldc = C;
+    a.M = (int)N; a.N = C; a.K = Cn; a.bias = dry ? nullptr : p->bnode;
+    YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
+    yolat_bn bnn = dry ? yolat_bn{} : p->bnn;
+    YOLAT_TRY(bn_forward_stats(t.zn, C, N, C, &bnn, training, t.statn, ws, st));
+    if (!dry) YOLAT_TRY(bn_apply(t.zn, C, N, C, t.statn, 1, xnode_out, ldxo, st));
+  }
+  if (!dry && ws.overflow) return YOLAT_ERR_WORKSPACE;
+  return YOLAT_OK;
+}
+
+static int zero_opt(float* p, int64_t n, cudaStream_t st) { return p ? fill_zero(p, n, st) : YOLAT_OK; }
+
+static int gp2_bwd_impl(const yolat_gp2_params* p, const yolat_gp2_grads* gr, int Cin, int Cn, int C, const float* x,
+                        int64_t ldx, const float* x_node, int64_t ldxn, const float* attr, const float* ew,
+                        const int32_t* graph, int64_t N, int64_t E, int training, const float* g_out, int64_t ldgo,
+                        const float* g_xnode, int64_t ldgx, float* dx, int64_t lddx, float* dx_node, int64_t lddxn,
+                        int accumulate_dx, Arena& tape, Arena& ws, cudaStream_t st) {
+  const bool dry = ws.dry();
+  Gp2Tape t;
+  gp2_tape_layout(tape, N, E, C, &t);
+  const int ld1 = 2 * Cin + 4;
+  yolat_gp2_grads G{};
+  if (!dry) G = *gr;
+  GraphView g;
+  if (!dry) graph_layout(N, E, graph, &g);
+  int acc_dx = accumulate_dx, acc_dxn = accumulate_dx;
+
+  // ---- node branch -------------------------------------------------------------------------------
+  {
+    float* dzn = ws.take(N * C);
+    BnBwdArgs b{};
+    b.gy = g_xnode; b.ldgy = ldgx; b.z = t.zn; b.ldz = C; b.M = N; b.C = C; b.stat = t.statn;
+    b.gamma = dry ? nullptr : p->bnn.w; b.relu = 1; b.training = training; b.dz = dzn; b.lddz = C;
+    b.dgamma = G.bnn_w; b.dbeta = G.bnn_b; b.dbias = G.bnode;
+    YOLAT_TRY(bn_backward(b, ws, st));
+    if (G.wn || dry) {
+      GemmArgs a{};
+      a.A = dzn; a.lda = C; a.B = x_node; a.ldb = ldxn; a.C = G.wn; a.ldc = Cn; a.M = C; a.N = Cn; a.K = N;
+      YOLAT_TRY(gemm(a, GEMM_TN, ws, st));
+    }
+    if (dx_node || dry) {
+      GemmArgs a{};
+      a.A = dzn; a.lda = C; a.B = dry ? nullptr : p->wn; a.ldb = Cn; a.C = dx_node; a.ldc = lddxn;
+      a.M = (int)N; a.N = Cn; a.K = C; a.accumulate = acc_dxn;
+      YOLAT_TRY(gemm(a, GEMM_NN, ws, st));
+      acc_dxn = 1;
+    }
+  }
+
+  // ---- lin_r --------------------------------------------------------------------------------------
+  if (G.wr || dry) {
+    GemmArgs a{};
+    a.A = g_out; a.lda = ldgo; a.B = x; a.ldb = ldx; a.C = G.wr; a.ldc = Cin; a.M = C; a.N = Cin; a.K = N;
+    YOLAT_TRY(gemm(a, GEMM_TN, ws, st));
+  }
+  if (G.br || dry) YOLAT_TRY(colsum(g_out, ldgo, N, C, G.br, ws, st));
+  if (dx || dry) {
+    GemmArgs a{};
+    a.A = g_out; a.lda = ldgo; a.B = dry ? nullptr : p->wr; a.ldb = Cin; a.C = dx; a.ldc = lddx;
+    a.M = (int)N; a.N = Cin; a.K = C; a.accumulate = acc_dx;
+    YOLAT_TRY(gemm(a, GEMM_NN, ws, st));
+    acc_dx = 1;
+  }
+
+  // ---- edge path ------------------------------------------------------------------------------------
+  if (E > 0) {
+    float* dz2 = ws.take(E * C);
+    float* dz1 = ws.take(E * C);
+    float* dpq = ws.take(N * 2 * C);
+    float* wpq = ws.take((int64_t)2 * C * Cin);
+    float* dwpq = ws.take((int64_t)2 * C * Cin);
+    float* dw1c = ws.take((int64_t)C * 4);
+    const int nparts = edge_z1_nparts(N);
+    float* partw = ws.take((int64_t)nparts * C * 4);
+    // BN2 + ReLU backward with the mean-aggregation gather fused in:
+    //   dy[slot] = g_out[dst[slot]] * deg_inv[dst[slot]] * edge_weight[eid[slot]]
+    {
+      BnBwdArgs b{};
+      b.gy = g_out; b.ldgy = ldgo; b.row_idx = dry ? nullptr : g.dst_t; b.row_scale = dry ? nullptr : g.deg_inv;
+      if (ew) { b.slot_idx = g.eid_t; b.slot_scale = ew; }
+      b.z = t.z2; b.ldz = C; b.M = E; b.C = C; b.stat = t.stat2; b.gamma = dry ? nullptr : p->bn2.w;
+      b.relu = 1; b.training = training; b.dz = dz2; b.lddz = C;
+      b.dgamma = G.bn2_w; b.dbeta = G.bn2_b; b.dbias = G.b2;
+      YOLAT_TRY(bn_backward(b, ws, st));
+    }
+    if (G.w2 || dry) {   // dW2 = dz2^T relu(bn1(z1))
+      GemmArgs a{};
+      a.A = dz2; a.lda = C; a.B = t.z1; a.ldb = C; a.C = G.w2; a.ldc = C; a.M = C; a.N = C; a.K = E;
+      a.b_sc = t.stat1; a.b_sh = dry ? nullptr : t.stat1 + C;
+      YOLAT_TRY(gemm(a, GEMM_TN, ws, st));
+    }
+    {                    // da1 = dz2 W2
+      GemmArgs a{};
+      a.A = dz2; a.lda = C; a.B = dry ? nullptr : p->w2; a.ldb = C; a.C = dz1; a.ldc = C;
+      a.M = (int)E; a.N = C; a.K = C;
+      YOLAT_TRY(gemm(a, GEMM_NN, ws, st));
+    }
+    {
+      BnBwdArgs b{};
+      b.gy = dz1; b.ldgy = C; b.z = t.z1; b.ldz = C; b.M = E; b.C = C; b.stat = t.stat1;
+      b.gamma = dry ? nullptr : p->bn1.w; b.relu = 1; b.training = training; b.dz = dz1; b.lddz = C;
+      b.dgamma = G.bn1_w; b.dbeta = G.bn1_b; b.dbias = G.b1;
+      YOLAT_TRY(bn_backward(b, ws, st));
+    }
+    if (!dry) YOLAT_TRY(edge_bwd_scatter(g, N, C, dz1, attr, dpq, partw, dw1c, st));
+    if (G.w1 || dry) {   // dWpq = dPQ^T x ; dW1 = [dWp | dWq - dWp | dW1c]
+      GemmArgs a{};
+      a.A = dpq; a.lda = 2 * C; a.B = x; a.ldb = ldx; a.C = dwpq; a.ldc = Cin; a.M = 2 * C; a.N = Cin; a.K = N;
+      YOLAT_TRY(gemm(a, GEMM_TN, ws, st));
+      if (!dry && G.w1) YOLAT_TRY(edge_assemble_dw1(dwpq, dw1c, Cin, C, G.w1, st));
+    }
+    if (dx || dry) {     // dx += dPQ Wpq
+      if (!dry) YOLAT_TRY(edge_prep_wpq(p->w1, Cin, C, wpq, st));
+      GemmArgs a{};
+      a.A = dpq; a.lda = 2 * C; a.B = wpq; a.ldb = Cin; a.C = dx; a.ldc = lddx;
+      a.M = (int)N; a.N = Cin; a.K = 2 * C; a.accumulate = acc_dx;
+      YOLAT_TRY(gemm(a, GEMM_NN, ws, st));
+    }
+  } else if (!dry) {
+    YOLAT_TRY(zero_opt(G.w1, (int64_t)C * ld1, st)); YOLAT_TRY(zero_opt(G.b1, C, st));
+    YOLAT_TRY(zero_opt(G.bn1_w, C, st)); YOLAT_TRY(zero_opt(G.bn1_b, C, st));
+    YOLAT_TRY(zero_opt(G.w2, (int64_t)C * C, st)); YOLAT_TRY(zero_opt(G.b2, C, st));
+    YOLAT_TRY(zero_opt(G.bn2_w, C, st)); YOLAT_TRY(zero_opt(G.bn2_b, C, st));
+  }
+  if (!dry && ws.overflow) return YOLAT_ERR_WORKSPACE;
+  return YOLAT_OK;
+}
+
+}  // namespace yolat
+
+using namespace yolat;
+
+extern "C" {
+
+int64_t yolat_gp2_tape_floats(int64_t N, int64_t E, int Cin, int Cn, int C) {
+  (void)Cin; (void)Cn;
+  Arena t(nullptr, 0);
+  Gp2Tape o;
+  gp2_tape_layout(t, N, E, C, &o);
+  return t.off;
+}
+
+int64_t yolat_gp2_fwd_ws_floats(int64_t N, int64_t E, int Cin, int Cn, int C) {
+  if (!gp2_channels_ok(Cin, Cn, C)) return -1;
+  Arena tape(nullptr, 0), ws(nullptr, 0);
+  gp2_fwd_impl(nullptr, Cin, Cn, C, nullptr, Cin, nullptr, Cn, nullptr, nullptr, nullptr, N, E, 1, nullptr, C, nullptr, C,
+               tape, ws, nullptr);
+  return ws.off;
+}
+
+int64_t yolat_gp2_bwd_ws_floats(int64_t N, int64_t E, int Cin, int Cn, int C) {
+  if (!gp2_channels_ok(Cin, Cn, C)) return -1;
+  Arena tape(nullptr, 0), ws(nullptr, 0);
+  gp2_bwd_impl(nullptr, nullptr, Cin, Cn, C, nullptr, Cin, nullptr, Cn, nullptr, nullptr, nullptr, N, E, 1, nullptr, C,
+               nullptr, C, nullptr, Cin, nullptr, Cn, 0, tape, ws, nullptr);
+  return ws.off;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int yolat_gp2_fwd(const yolat_gp2_params* p, int Cin, int Cn, int C, const float* x, int64_t ldx, const float* x_node,
+                  int64_t ldxn, const float* attr, const float* edge_weight, const int32_t* graph, int64_t N, int64_t E,
+                  int training, float* out, int64_t ldo, float* xnode_out, int64_t ldxo, float* tape, int64_t tape_floats,
+                  float* ws, int64_t ws_floats, void* stream) {
+  if (!p || !x || !x_node || !graph || !out || !xnode_out || !tape || !ws || N <= 0 || E < 0) return YOLAT_ERR_INVALID;
+  if (E > 0 && (!attr || !aligned16(attr))) return YOLAT_ERR_INVALID;
+  if (!gp2_channels_ok(Cin, Cn, C)) return YOLAT_ERR_UNSUPPORTED;
+  if (tape_floats < yolat_gp2_tape_floats(N, E, Cin, Cn, C)) return YOLAT_ERR_WORKSPACE;
+  Arena t(tape, tape_floats), w(ws, ws_floats);
+  return gp2_fwd_impl(p, Cin, Cn, C, x, ldx, x_node, ldxn, attr, edge_weight, graph, N, E, training, out, ldo, xnode_out,
+                      ldxo, t, w, (cudaStream_t)stream);
+}
+
+int yolat_gp2_bwd(const yolat_gp2_params* p, const yolat_gp2_grads* g, int Cin, int Cn, int C, const float* x, int64_t ldx,
+                  const float* x_node, int64_t ldxn, const float* attr, const float* edge_weight, const int32_t* graph,
+                  int64_t N, int64_t E, int training, const float* g_out, int64_t ldgo, const float* g_xnode, int64_t ldgx,
+                  float* dx, int64_t lddx, float* dx_node, int64_t lddxn, int accumulate_dx, const float* tape, float* ws,
+                  int64_t ws_floats, void* stream) {
+  if (!p || !g || !x || !x_node || !graph || !tape || !ws || !g_out || !g_xnode || N <= 0 || E < 0) return YOLAT_ERR_INVALID;
+  if (E > 0 && (!attr || !aligned16(attr))) return YOLAT_ERR_INVALID;
+  if (!gp2_channels_ok(Cin, Cn, C)) return YOLAT_ERR_UNSUPPORTED;
+  Arena t(const_cast<float*>(tape), yolat_gp2_tape_floats(N, E, Cin, Cn, C)), w(ws, ws_floats);
+  return gp2_bwd_impl(p, g, Cin, Cn, C, x, ldx, x_node, ldxn, attr, edge_weight, graph, N, E, training, g_out, ldgo,
+                      g_xnode, ldgx, dx, lddx, dx_node, lddxn, accumulate_dx, t, w, (cudaStream_t)stream);
+}
+
+}  // extern "C"
