@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- Bezier graphs/s, fwd + loss + bwd of YOLaT's proposal classifier, on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a engine
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+
+One "step" = SparseCADGCN.forward + DetectionLoss + backward over one batch of synthetic
+Floorplans-shaped graphs (BASELINE.json configs[1]: batch 4 x 5 000 nodes / 20 000 edges, in_channels 5,
+n_blocks 2).  At N > 1 every rank runs the same batch shape on its own seed (weak scaling) and the step
+ends with one NCCL all-reduce of the flat gradient buffer.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = 'floorplans-shaped synthetic: batch 4 x (5000 nodes, 20000 edges), 16-node proposals (B=1250)'
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--graphs', type=int, default=4, help='graphs per rank per step')
+    ap.add_argument('--cpu-steps', type=int, default=8, help='timed steps of the cpu_baseline leg')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--scatter-graphs', type=int, default=64,
+                    help='graphs in the > L2 K-EDGE roofline measurement (0 = use the step workload)')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm (the reference tree itself cannot travel to the box)
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(graphs, steps, warmup):
+    from oracle import restatement as R
+    from yolat_vectorgraphicsrecognition_b200 import synth
+    from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    opt = synth.make_opt(n_classes=17)
+    torch.manual_seed(0)
+    state = R.clone_state(arch.SparseCADGCN(opt).state_dict(), torch.float32)
+    batch = synth.floorplans_batch(graphs=graphs, seed=1)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        R.run_step(state, opt, batch, training=True)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return dict(value=graphs / med, unit='graphs/s', cores=cores, kind='port',
+                sample='%d timed fwd+bwd steps (median) of the full step workload (%d graphs), oracle/restatement.py, '
+                       'torch %s CPU fp32, %d threads' % (steps, graphs, torch.__version__, cores)), med
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    base, med = cpu_reference_run(args.graphs, max(1, min(args.steps, 10)), max(1, min(args.warmup, 3)))
+    line = {
+        'impl': 'reference', 'metric': 'graphs_per_sec_fwd_bwd', 'value': base['value'], 'unit': 'graphs/s',
+        'n_gpus': args.gpus, 'steps': max(1, min(args.steps, 10)), 'warmup': max(1, min(args.warmup, 3)),
+        'ms_per_step': med * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'step': 'fwd+loss+bwd', 'graphs_per_step': args.graphs},
+        'cpu_baseline': base,
+        'e2e': {'value': base['value'], 'unit': 'graphs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------------
+class Clocks(object):
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], None, set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for r in rows:
+            f = [x.strip() for x in r.split(',')]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except Exception:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def edge_bytes(N, E, Cin, Cn, C):
+    """Algorithmic bytes of one GraphConv('attr_edge_gp2') forward: x + edge_index (int64 as
+    delivered) + e_attr + out, plus the node branch x_node + x_node_out."""
+    return 4 * N * Cin + 16 * E + 16 * E + 4 * N * C + 4 * N * Cn + 4 * N * C
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    from yolat_vectorgraphicsrecognition_b200 import _lib, synth, ops
+    from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
+    from yolat_vectorgraphicsrecognition_b200.graph import CSRGraph
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl b200 needs a CUDA device (no CPU fallback)')
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.lib()
+
+    opt = synth.make_opt(n_classes=17)
+    torch.manual_seed(0)
+    model = arch.SparseCADGCN(opt).to(dev).train()
+    crit = arch.DetectionLoss(opt)
+    params = [p for p in model.parameters()]
+    host = synth.floorplans_batch(graphs=args.graphs, seed=1 if world == 1 else 1000 + rank).pin_memory()
+    resident = host.to(dev)
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+
+    def step(batch):
+        for p in params:
+            p.grad = None
+        out = model(batch, None)
+        loss = crit(out, batch)['loss']
+        loss.backward()
+        if world > 1:
+            flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
+            dist.all_reduce(flat)
+            flat.mul_(1.0 / world)
+            for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, params)):
+                p.grad = g
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: value ------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    barrier()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    launches0 = lib.yolat_launch_count()
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()                    # evict L2 between timed steps (untimed)
+        a.record()
+        step(resident)
+        b.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = (lib.yolat_launch_count() - launches0) // max(args.steps, 1)
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # ---- end to end through the public API with host buffers: e2e -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(3):
+            float(step(host))
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            loss = step(host)            # .cuda() copies of the pinned host tensors happen inside forward / loss
+            float(loss)                  # D2H read of the step's result (train.py:286)
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d = sum(getattr(host, n).numel() * getattr(host, n).element_size()
+                  for n in ('x', 'bbox_idx', 'edge', 'bbox', 'e_attr', 'labels'))
+        e2e = {'value': args.graphs * world / (float(t.item()) * 1e-3), 'unit': 'graphs/s',
+               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'ms_per_step': float(t.item())}
+
+    # ---- roofline of the scatter path: one block-layer GraphConv forward (edge + node branch) -----------
+    roof = None
+    if rank == 0:
+        hbm, which = peaks()
+        sg = args.scatter_graphs if args.scatter_graphs > 0 else args.graphs
+        big = synth.floorplans_batch(graphs=sg, seed=7).to(dev)
+        Nn, Ee = big.x.shape[0], big.edge.shape[0]
+        conv = model.cls_net.backbone[0].body
+        xin = torch.randn(Nn, 64, device=dev)
+        xnode = torch.randn(Nn, 64, device=dev)
+        graph = CSRGraph(big.edge.T, Nn)
+        with torch.no_grad():
+            for _ in range(3):
+                conv(xin, graph, None, big.e_attr, x_node=xnode)
+            reps, tot = 10, 0.0
+            for _ in range(reps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                conv(xin, graph, None, big.e_attr, x_node=xnode)
+                b.record()
+                torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+        k_ms = tot / reps
+        nbytes = edge_bytes(Nn, Ee, 64, 64, 64)
+        ach = nbytes / (k_ms * 1e-3) / 1e9
+        roof = {'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None,
+                'kernel': 'yolat_gp2_fwd (block layer 64->64, training): gather + edge MLP + BN + mean-scatter + node branch',
+                'algorithmic_bytes': nbytes, 'ms': k_ms, 'peak_source': which,
+                'shape': {'N': Nn, 'E': Ee, 'graphs': sg}, 'l2': 'flushed before every launch'}
+        del big, xin, xnode, graph
+
+    # ---- CPU baseline (rank 0, N = 1) -------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_reference_run(args.graphs, args.cpu_steps, 2)
+
+    if rank == 0:
+        line = {
+            'metric': 'graphs_per_sec_fwd_bwd', 'value': args.graphs * world / (ms * 1e-3), 'unit': 'graphs/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'step': 'fwd+loss+bwd' + ('+nccl grad all-reduce' if world > 1 else ''),
+                       'graphs_per_step_per_gpu': args.graphs, 'in_channels': 5, 'n_blocks': 2, 'n_filters': 64,
+                       'n_classes': 17, 'l2': 'flushed between timed steps (256 MiB memset, untimed)',
+                       'parallelism': 'dp%d' % world},
+            'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

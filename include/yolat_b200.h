@@ -35,6 +35,8 @@ int yolat_abi_version(void);
 const char* yolat_status_string(int status);
 /* last CUDA error string seen by a failing launch on this thread (diagnostics only) */
 const char* yolat_last_cuda_error(void);
+/* number of kernels this library has launched in this process (bench.py reports the per-step delta) */
+int64_t yolat_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Graph preparation.  Replaces what PyG's MessagePassing.propagate does implicitly on every call
@@ -168,7 +170,7 @@ int yolat_fusemax_bwd(const float* feats, int64_t ldf, int64_t M, int K, const f
 /* ------------------------------------------------------------------------------------------------
  * CrossEntropyLoss(mean) (architecture3cc_rpn_gp_iter2.py:363,376).  prob [B,ncls] is the tape.
  * bwd: dlogits = (softmax - onehot) * (*g_loss) / B, g_loss a DEVICE scalar (no host sync).
- * Labels outside [0,ncls) contribute 0 and are counted in *bad_labels if non-NULL.
+ * Labels outside [0,ncls) contribute 0 to the loss and get a zero gradient row.
  * ---------------------------------------------------------------------------------------------- */
 int yolat_softmax_xent_fwd(const float* logits, int64_t ldl, int64_t B, int ncls, const int64_t* labels,
                            float* loss, float* prob, float* ws, int64_t ws_floats, void* stream);

@@ -147,7 +147,7 @@ def conv_fixture(arch, name, N, E, Cin, C, seed, with_weight=False, zero_edges=F
             res['buffers_after64'] = c_after
             res['eval_out64'], res['eval_xnode64'] = eo.detach(), en.detach()
         # restatement check
-        st = {('c.' + k): v.to(dt) if v.is_floating_point() else v.clone() for k, v in sd.items()}
+        st = {('c.' + k): v.clone().to(dt) if v.is_floating_point() else v.clone() for k, v in sd.items()}
         st = {k.replace('c.gconv', 'c'): v for k, v in st.items()}
         ro, rn = R.gp2_conv(st, 'c', xx.detach(), xxn.detach(), edge.t(), attr.to(dt), True,
                             None if w is None else w.to(dt))

@@ -48,7 +48,7 @@ def test_model_step_matches_reference(name):
     loss.backward()
     assert out[0].shape == fx['logits64'].shape and torch.equal(out[1].cpu(), batch.bbox)
     assert max_rel(out[0], fx['logits64']) < FWD_TOL, max_rel(out[0], fx['logits64'])
-    assert abs(float(loss) - fx['loss64']) < FWD_TOL * max(1.0, abs(fx['loss64']))
+    assert abs(float(loss.detach()) - fx['loss64']) < FWD_TOL * max(1.0, abs(fx['loss64']))
     worst = {}
     for k, p in model.named_parameters():
         ref = fx['grad64_sample'][k]

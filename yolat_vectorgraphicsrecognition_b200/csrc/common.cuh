@@ -15,10 +15,12 @@ constexpr float kBnMomentum = 0.1f;
 constexpr int kNumSMs = 148;          // B200
 
 void set_last_error(cudaError_t e);
+void count_launch();   // process-wide kernel-launch counter behind yolat_launch_count()
 
 #define YOLAT_CHECK_LAUNCH()                                  \
   do {                                                        \
     cudaError_t _e = cudaGetLastError();                      \
+    ::yolat::count_launch();                                  \
     if (_e != cudaSuccess) {                                  \
       ::yolat::set_last_error(_e);                            \
       return YOLAT_ERR_LAUNCH;                                \

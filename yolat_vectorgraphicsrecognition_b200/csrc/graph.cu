@@ -5,12 +5,15 @@
 // (cad_recognition/architecture3cc_rpn_gp_iter2.py:67,122).  The result is deterministic: inside a
 // row, slots are ordered by original edge id (rows are sorted after the atomic fill), so every
 // segmented reduction downstream has a fixed summation order.
+#include <atomic>
 #include "common.cuh"
 
 namespace yolat {
 
 static thread_local cudaError_t g_last = cudaSuccess;
 void set_last_error(cudaError_t e) { g_last = e; }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- counting --------------------------------------------------------------------------------
 __global__ void k_count_edges(const int64_t* __restrict__ edge, int64_t se, int64_t sc, int64_t E, int64_t N,
@@ -160,6 +163,8 @@ using namespace yolat;
 extern "C" {
 
 int yolat_abi_version(void) { return 1; }
+
+int64_t yolat_launch_count(void) { return (int64_t)yolat::g_launches.load(std::memory_order_relaxed); }
 
 const char* yolat_status_string(int s) {
   switch (s) {
