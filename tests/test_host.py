@@ -1,0 +1,96 @@
+"""CPU: host-side mirror of the reference interface -- module tree, state-dict keys, construction-order
+RNG parity, stage grouping, error behaviour, synthetic batch layouts, sharding helper."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import restatement as R
+from yolat_vectorgraphicsrecognition_b200 import synth, dp
+from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
+from yolat_vectorgraphicsrecognition_b200.gcn_lib import sparse as gl
+
+
+def test_state_dict_keys_and_shapes_match_reference_layout():
+    for kw in (dict(n_classes=17), dict(n_classes=22, n_blocks=3, n_blocks_out=2), dict(n_classes=3, n_blocks=1, n_blocks_out=1)):
+        opt = synth.make_opt(**kw)
+        sd = arch.SparseCADGCN(opt).state_dict()
+        spec = R.state_spec(opt)
+        assert [k for k, _, _ in spec] == list(sd.keys())
+        for k, shape, _ in spec:
+            assert tuple(sd[k].shape) == tuple(shape), k
+    assert sum(p.numel() for p in arch.SparseCADGCN(synth.make_opt(n_classes=17)).parameters()) == 1613329
+
+
+def test_attribute_paths():
+    m = arch.SparseCADGCN(synth.make_opt(n_classes=17))
+    assert isinstance(m.cls_net.head.gconv.nn, gl.MLP) and isinstance(m.cls_net.backbone[0].body.gconv.lin_r, torch.nn.Linear)
+    assert len(m.cls_net.heads) == 0 and m.cls_net.fusion_dims == 128 and m.dim_stat == 0
+    assert [type(c).__name__ for c in m.cls_net.head.gconv.nn] == ['Linear', 'BatchNorm1d', 'ReLU'] * 2
+    assert [type(c).__name__ for c in m.prediction_cls[2]] == ['Linear']
+
+
+def test_mlp_constructor_semantics():
+    assert [type(c).__name__ for c in gl.MLP([4, 8, 3], 'relu', 'batch', last_lin=True)] == ['Linear', 'BatchNorm1d', 'ReLU', 'Linear']
+    assert [type(c).__name__ for c in gl.MLP([4, 8], 'leakyrelu', 'layer', drop=0.5)] == ['Linear', 'LayerNorm', 'LeakyReLU', 'Dropout2d']
+    assert gl.MLP([4, 8], None, 'none', bias=False)[0].bias is None
+    st = gl.MLP([4, 8, 3], 'relu', 'batch', last_lin=True).stages()
+    assert [s[0] for s in st] == ['stage', 'stage'] and st[0][2] is not None and st[0][3] and st[1][2] is None
+    with pytest.raises(NotImplementedError):
+        gl.act_layer('gelu')
+    with pytest.raises(NotImplementedError):
+        gl.norm_layer('group', 8)
+
+
+def test_graphconv_dispatch_errors():
+    with pytest.raises(NotImplementedError, match='conv foo is not implemented'):
+        gl.GraphConv(4, 8, 'foo')
+    with pytest.raises(NotImplementedError):
+        gl.GraphConv(4, 8, 'edge')
+    with pytest.raises(NotImplementedError):
+        gl.PlainDynBlock(8)
+    c = gl.GraphConv(5, 64, 'ATTR_EDGE_GP2', act='prelu', norm='layer', bias=False)   # act/norm/bias ignored (:749)
+    assert c.conv == 'attr_edge_gp2' and c.gconv.lin_r.bias is not None
+
+
+def test_multiseq_splats_tuples():
+    class Two(torch.nn.Module):
+        def forward(self, a, b=None):
+            return (a + 1, a * 2) if b is None else a + b
+    assert float(gl.MultiSeq(Two(), Two())(torch.tensor(1.0))) == 4.0
+
+
+def test_no_cpu_path():
+    from yolat_vectorgraphicsrecognition_b200 import _lib
+    with pytest.raises(_lib.YolatError):
+        gl.MLP([8, 8], 'relu', 'batch')(torch.randn(4, 8))
+    with pytest.raises(_lib.YolatError):
+        from yolat_vectorgraphicsrecognition_b200.torch_scatter import scatter
+        scatter(torch.randn(4, 2), torch.tensor([0, 0, 1, 1]), dim=0, reduce='max')
+
+
+def test_synthetic_layouts():
+    b = synth.floorplans_batch()
+    assert b.x.shape == (20000, 5) and b.edge.shape == (80000, 2) and b.e_attr.shape == (80000, 4)
+    assert b.bbox.shape == (1250, 4) and b.labels.shape == (1250,) and b.edge.dtype == torch.int64
+    assert bool((b.bbox_idx[1:] >= b.bbox_idx[:-1]).all()) and int(b.bbox_idx[-1]) == 1249
+    assert bool((b.bbox_idx[b.edge[:, 0]] == b.bbox_idx[b.edge[:, 1]]).all())      # edges never cross proposals
+    assert bool((b.x[:, :3] == 0).all())
+    t = synth.toy_batch()
+    assert t.x.shape == (128, 5) and int(t.labels.max()) <= 2
+    d = synth.diagrams_batch(graphs=1, n=300, e=900)
+    cnt = torch.bincount(d.bbox_idx)
+    assert int(cnt.min()) >= 1 and d.bbox.shape[0] == cnt.numel()
+    h = synth.hierarchical_batch()
+    assert h.x.shape[0] == 15000 and h.edge.shape[0] == 50000 and int(h.bbox_idx[-1]) == 499
+    assert torch.equal(synth.floorplans_batch(graphs=1, seed=5).edge, synth.floorplans_batch(graphs=1, seed=5).edge)
+
+
+def test_shard_graphs():
+    for n, w in ((32, 8), (7, 4), (4, 1), (3, 4)):
+        parts = [dp.shard_graphs(n, w, r) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    edges = [10, 10, 10, 70, 10, 10, 10, 10]
+    parts = [dp.shard_graphs(8, 2, r, edges) for r in range(2)]
+    assert parts == [(0, 4), (4, 8)]
