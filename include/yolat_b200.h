@@ -117,6 +117,18 @@ int yolat_gp2_bwd(const yolat_gp2_params* p, const yolat_gp2_grads* g, int Cin, 
                   const float* tape, float* ws, int64_t ws_floats, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * The dense building block under every nn.Linear on the path (gcn_lib/sparse/torch_nn.py:58 and its autograd):
+ * C[M,N] (+)= op(A) op(B) (+ bias[n]) on the tcgen05 tensor cores with fp32-accurate 3xTF32 splitting.
+ *   mode 0 (NT): A[m*lda+k], B[n*ldb+k]   y  = x W^T + b
+ *   mode 1 (NN): A[m*lda+k], B[k*ldb+n]   dx = dy W
+ *   mode 2 (TN): A[k*lda+m], B[k*ldb+n]   dW = dy^T x   (K = number of rows reduced over)
+ * ---------------------------------------------------------------------------------------------- */
+int64_t yolat_gemm_ws_floats(int mode, int64_t M, int64_t N, int64_t K);
+int yolat_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+               int64_t M, int64_t N, int64_t K, const float* bias, int accumulate,
+               float* ws, int64_t ws_floats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * One [Lin, BN?, ReLU?] stage of gcn_lib.sparse.MLP (torch_nn.py:50-71): y = act(bn(x W^T + b)).
  * flags: bit0 = has BatchNorm, bit1 = has ReLU, bit2 = training.
  * tape: z [M,Nout] (pre-BN) + 4*Nout statistics when BN is present.

@@ -38,18 +38,37 @@ __global__ void __launch_bounds__(ST_COLS* ST_ROWS) k_colstats(const float* __re
   }
 }
 
-__global__ void k_bn_finalize(const float* __restrict__ part, int nparts, int64_t M, int C, yolat_bn bn, int training,
-                              float* __restrict__ stat) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && training && bn.num_batches_tracked) *bn.num_batches_tracked += 1;
-  if (c >= C) return;
+// Sum part[p][w][C] over p (fp64) for w = 0,1 with a 32 x 32 thread block: tx = channel (coalesced 128-byte rows),
+// ty strides over the partials.  The result is valid in the ty == 0 threads.
+__device__ __forceinline__ void reduce_parts2(const float* __restrict__ part, int nparts, int C, int c, double& s, double& t) {
+  __shared__ double sm[2][32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int p = ty; p < nparts; p += 32) {
+      a += (double)part[((int64_t)p * 2 + 0) * C + c];
+      b += (double)part[((int64_t)p * 2 + 1) * C + c];
+    }
+  }
+  sm[0][ty][tx] = a; sm[1][ty][tx] = b;
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll 4
+    for (int q = 1; q < 32; ++q) { a += sm[0][q][tx]; b += sm[1][q][tx]; }
+  }
+  s = a; t = b;
+}
+
+__global__ void __launch_bounds__(1024) k_bn_finalize(const float* __restrict__ part, int nparts, int64_t M, int C,
+                                                      yolat_bn bn, int training, float* __restrict__ stat) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && training && bn.num_batches_tracked)
+    *bn.num_batches_tracked += 1;
+  double s = 0.0, ss = 0.0;
+  if (training) reduce_parts2(part, nparts, C, c, s, ss);
+  if (threadIdx.y != 0 || c >= C) return;
   float mean, var;
   if (training) {
-    double s = 0.0, ss = 0.0;
-    for (int p = 0; p < nparts; ++p) {
-      s += (double)part[((int64_t)p * 2 + 0) * C + c];
-      ss += (double)part[((int64_t)p * 2 + 1) * C + c];
-    }
     const double mu = s / (double)M;
     double v = ss / (double)M - mu * mu;
     if (v < 0.0) v = 0.0;
@@ -74,9 +93,26 @@ __global__ void k_bn_finalize(const float* __restrict__ part, int nparts, int64_
 
 int bn_finalize_from_partials(const float* part, int nparts, int64_t M, int C, const yolat_bn* bn, int training,
                               float* stat, cudaStream_t st) {
-  k_bn_finalize<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(part, nparts, M, C, *bn, training, stat);
+  k_bn_finalize<<<(unsigned)cdiv(C, 32), dim3(32, 32), 0, st>>>(part, nparts, M, C, *bn, training, stat);
   YOLAT_CHECK_LAUNCH();
   return YOLAT_OK;
+}
+
+// z = x W^T + b through the tensor-core GEMM with the BatchNorm statistics taken from the GEMM's own epilogue
+// (per-tile column sums) when the kernel produced them, otherwise from a separate pass over z.
+int linear_bn_stats(const GemmArgs& a, Arena& ws, const yolat_bn* bn, int training, float* stat, cudaStream_t st) {
+  float* part = nullptr;
+  int np = 0;
+  if (training) {
+    YOLAT_TRY(gemm_stats(a, GEMM_NT, ws, &part, &np, st));
+  } else {
+    YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
+  }
+  if (training && np > 0) {
+    if (ws.dry()) return YOLAT_OK;
+    return bn_finalize_from_partials(part, np, a.M, a.N, bn, training, stat, st);
+  }
+  return bn_forward_stats(a.C, a.ldc, a.M, a.N, bn, training, stat, ws, st);
 }
 
 int bn_forward_stats(const float* z, int64_t ldz, int64_t M, int C, const yolat_bn* bn, int training, float* stat,
@@ -151,17 +187,15 @@ __global__ void __launch_bounds__(ST_COLS* ST_ROWS) k_bn_bwd_partial(BnBwdArgs a
 }
 
 // bstat: [0] m1 = sum(dy')/M, [1] m2 = sum(dy'*xhat)/M  (both 0 in eval mode: statistics are constants)
-__global__ void k_bn_bwd_finalize(const float* __restrict__ part, int nparts, int64_t M, int C,
-                                  const float* __restrict__ stat, const float* __restrict__ gamma, int training,
-                                  float* __restrict__ bstat, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                  float* __restrict__ dbias) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, t = 0.0;
-  for (int p = 0; p < nparts; ++p) {
-    s += (double)part[((int64_t)p * 2 + 0) * C + c];
-    t += (double)part[((int64_t)p * 2 + 1) * C + c];
-  }
+__global__ void __launch_bounds__(1024) k_bn_bwd_finalize(const float* __restrict__ part, int nparts, int64_t M, int C,
+                                                          const float* __restrict__ stat, const float* __restrict__ gamma,
+                                                          int training, float* __restrict__ bstat,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                          float* __restrict__ dbias) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, t;
+  reduce_parts2(part, nparts, C, c, s, t);
+  if (threadIdx.y != 0 || c >= C) return;
   if (dgamma) dgamma[c] = (float)t;
   if (dbeta) dbeta[c] = (float)s;
   if (training) {
@@ -191,7 +225,7 @@ __global__ void k_bn_bwd_apply(BnBwdArgs a, const float* __restrict__ bstat) {
 
 int bn_bwd_finalize(const float* part, int nparts, int64_t M, int C, const float* stat, const float* gamma, int training,
                     float* bstat, float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
-  k_bn_bwd_finalize<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(part, nparts, M, C, stat, gamma, training, bstat, dgamma,
+  k_bn_bwd_finalize<<<(unsigned)cdiv(C, 32), dim3(32, 32), 0, st>>>(part, nparts, M, C, stat, gamma, training, bstat, dgamma,
                                                             dbeta, dbias);
   YOLAT_CHECK_LAUNCH();
   return YOLAT_OK;
@@ -233,11 +267,18 @@ __global__ void __launch_bounds__(ST_COLS* ST_ROWS) k_colsum_partial(const float
     part[(int64_t)blockIdx.y * C + c] = a;
   }
 }
-__global__ void k_colsum_final(const float* __restrict__ part, int nparts, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(1024) k_colsum_final(const float* __restrict__ part, int nparts, int C,
+                                                       float* __restrict__ out) {
+  __shared__ double sm[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += (double)part[(int64_t)p * C + c];
+  if (c < C)
+    for (int p = ty; p < nparts; p += 32) s += (double)part[(int64_t)p * C + c];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty != 0 || c >= C) return;
+  for (int q = 1; q < 32; ++q) s += sm[q][tx];
   out[c] = (float)s;
 }
 
@@ -249,7 +290,7 @@ int colsum(const float* a, int64_t lda, int64_t M, int C, float* out, Arena& ws,
   dim3 grid((unsigned)cdiv(C, ST_COLS), nparts);
   k_colsum_partial<<<grid, ST_COLS * ST_ROWS, 0, st>>>(a, lda, M, C, part);
   YOLAT_CHECK_LAUNCH();
-  k_colsum_final<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(part, nparts, C, out);
+  k_colsum_final<<<(unsigned)cdiv(C, 32), dim3(32, 32), 0, st>>>(part, nparts, C, out);
   YOLAT_CHECK_LAUNCH();
   return YOLAT_OK;
 }

@@ -159,12 +159,19 @@ struct GemmArgs {
   const float* b_sh;
   int accumulate;          // C += result
 };
-// ws: split-K partials; returns needed floats when arena is dry
+// ws: split-K partials; returns needed floats when arena is dry.  Default: tcgen05 3xTF32 kernel (gemm_tc.cu).
 int gemm(const GemmArgs& a, GemmMode mode, Arena& ws, cudaStream_t st);
+int gemm_simt(const GemmArgs& a, GemmMode mode, Arena& ws, cudaStream_t st);
+// Same as gemm(), and additionally leaves per-row-tile column statistics of C (sum, sum of squares) in
+// *stat_part [*nparts][2][N] (taken from ws).  *nparts == 0: not produced (split-K or SIMT path) -- the caller
+// then runs the separate statistics pass over C.
+int gemm_stats(const GemmArgs& a, GemmMode mode, Arena& ws, float** stat_part, int* nparts, cudaStream_t st);
 
 // column statistics of z [M,C] -> BN stat block (+ running-stat update when training)
 int bn_forward_stats(const float* z, int64_t ldz, int64_t M, int C, const yolat_bn* bn, int training,
                      float* stat /*[4C]*/, Arena& ws, cudaStream_t st);
+// z = x W^T + b (a.C = z) followed by the BN statistic block of z; statistics come from the GEMM epilogue when possible
+int linear_bn_stats(const GemmArgs& a, Arena& ws, const yolat_bn* bn, int training, float* stat, cudaStream_t st);
 // finalize from externally produced partial sums: part [nparts][2][C] (sum, sumsq)
 int bn_finalize_from_partials(const float* part, int nparts, int64_t M, int C, const yolat_bn* bn, int training,
                               float* stat, cudaStream_t st);

@@ -74,10 +74,9 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
       a.A = t.z1; a.lda = C; a.B = dry ? nullptr : p->w2; a.ldb = C; a.C = t.z2; a.ldc = C;
       a.M = (int)E; a.N = C; a.K = C; a.bias = dry ? nullptr : p->b2;
       a.a_sc = t.stat1; a.a_sh = dry ? nullptr : t.stat1 + C;
-      YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
+      yolat_bn bn2 = dry ? yolat_bn{} : p->bn2;
+      YOLAT_TRY(linear_bn_stats(a, ws, &bn2, training, t.stat2, st));
     }
-    yolat_bn bn2 = dry ? yolat_bn{} : p->bn2;
-    YOLAT_TRY(bn_forward_stats(t.z2, C, E, C, &bn2, training, t.stat2, ws, st));
     if (!dry) YOLAT_TRY(edge_agg(g, N, C, t.z2, t.stat2, ew, out, ldo, st));
   }
   // ---- node path: mlp_node(x_node)  (torch_vertex.py:326) -----------------------------------------
@@ -85,9 +84,8 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
     GemmArgs a{};
     a.A = x_node; a.lda = ldxn; a.B = dry ? nullptr : p->wn; a.ldb = Cn; a.C = t.zn; a.ldc = C;
     a.M = (int)N; a.N = C; a.K = Cn; a.bias = dry ? nullptr : p->bnode;
-    YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
     yolat_bn bnn = dry ? yolat_bn{} : p->bnn;
-    YOLAT_TRY(bn_forward_stats(t.zn, C, N, C, &bnn, training, t.statn, ws, st));
+    YOLAT_TRY(linear_bn_stats(a, ws, &bnn, training, t.statn, st));
     if (!dry) YOLAT_TRY(bn_apply(t.zn, C, N, C, t.statn, 1, xnode_out, ldxo, st));
   }
   if (!dry && ws.overflow) return YOLAT_ERR_WORKSPACE;

@@ -205,12 +205,19 @@ k_edge_bwd_scatter(GraphView g, int64_t N, const float* __restrict__ dz1, const 
   }
 }
 
-// out[t] = sum_p part[p][t]   (fp64 combine)
-__global__ void k_reduce_parts(const float* __restrict__ part, int nparts, int L, float* __restrict__ out) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= L) return;
+// out[t] = sum_p part[p][t]   (fp64 combine); 32 x 32 block: tx = element, ty strides over the partials
+__global__ void __launch_bounds__(1024) k_reduce_parts(const float* __restrict__ part, int nparts, int L,
+                                                       float* __restrict__ out) {
+  __shared__ double sm[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int t = blockIdx.x * 32 + tx;
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += (double)part[(int64_t)p * L + t];
+  if (t < L)
+    for (int p = ty; p < nparts; p += 32) s += (double)part[(int64_t)p * L + t];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty != 0 || t >= L) return;
+  for (int q = 1; q < 32; ++q) s += sm[q][tx];
   out[t] = (float)s;
 }
 
@@ -270,7 +277,7 @@ int edge_bwd_scatter(const GraphView& g, int64_t N, int C, const float* dz1, con
     default: return YOLAT_ERR_UNSUPPORTED;
   }
   YOLAT_CHECK_LAUNCH();
-  k_reduce_parts<<<(unsigned)cdiv(C * 4, 128), 128, 0, st>>>(part, grid, C * 4, dw1c);
+  k_reduce_parts<<<(unsigned)cdiv(C * 4, 32), dim3(32, 32), 0, st>>>(part, grid, C * 4, dw1c);
   YOLAT_CHECK_LAUNCH();
   return YOLAT_OK;
 }

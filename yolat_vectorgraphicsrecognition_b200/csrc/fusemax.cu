@@ -27,9 +27,8 @@ static int fm_fwd_impl(const float* feats, int64_t ldf, int64_t M, int K, const 
   if (!dry && tape.overflow) return YOLAT_ERR_WORKSPACE;
   GemmArgs a{};
   a.A = feats; a.lda = ldf; a.B = w; a.ldb = K; a.C = t.z; a.ldc = F; a.M = (int)M; a.N = F; a.K = K; a.bias = b;
-  YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
   yolat_bn bb = dry ? yolat_bn{} : *bn;
-  YOLAT_TRY(bn_forward_stats(t.z, F, M, F, &bb, training, t.stat, ws, st));
+  YOLAT_TRY(linear_bn_stats(a, ws, &bb, training, t.stat, st));
   if (!dry) {
     SegView sv;
     seg_layout(M, S, seg, &sv);

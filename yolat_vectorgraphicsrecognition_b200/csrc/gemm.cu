@@ -1,7 +1,7 @@
 // gemm.cu -- fp32 SIMT GEMM with fused BN+ReLU operand prologues, bias epilogue and deterministic split-K.
 //
-// This is the exact-fp32 path used for every Linear on the hot path whose shape the tcgen05 3xTF32
-// kernel (gemm_tc.cu) does not take:  y = x W^T + b  (gcn_lib/sparse/torch_nn.py:58),
+// Exact-fp32 reference kernel, selected with YOLAT_GEMM=simt (debugging aid; the default path is the tcgen05
+// 3xTF32 kernel in gemm_tc.cu):  y = x W^T + b  (gcn_lib/sparse/torch_nn.py:58),
 // dx = dy W and dW = dy^T x (autograd of the same).  Tiles: 64x64x16, 256 threads, 4x4 per thread.
 #include "common.cuh"
 
@@ -163,7 +163,7 @@ __global__ void k_bias_fill(int M, int N, const float* __restrict__ bias, float*
   if (accumulate) *c += v; else *c = v;
 }
 
-int gemm(const GemmArgs& a, GemmMode mode, Arena& ws, cudaStream_t st) {
+int gemm_simt(const GemmArgs& a, GemmMode mode, Arena& ws, cudaStream_t st) {
   if (a.M <= 0 || a.N <= 0) return YOLAT_OK;
   const int gm = (int)cdiv(a.M, BM), gn = (int)cdiv(a.N, BN);
   // split-K: enough CTAs to cover the machine ~2x, chunks multiple of BK, at least 8 k-tiles per chunk

@@ -1,0 +1,567 @@
+// gemm_tc.cu -- tcgen05 (5th-generation tensor core) GEMM with TMEM accumulators and fp32-accurate
+// 3xTF32 operand splitting, for every Linear on the hot path:
+//     y  = x W^T + b   (gcn_lib/sparse/torch_nn.py:58)        NT
+//     dx = dy W                                               NN
+//     dW = dy^T x                                             TN   (reduction over rows, deterministic split-K)
+//
+// Why 3xTF32: the parity bar is 1e-4 against an fp32 reference (BASELINE.json), kind::tf32 alone gives
+// ~1e-3.  Each operand is split in registers into hi = rn_tf32(v) and lo = v - hi (exact in fp32) and the
+// product is accumulated as  Ahi*Bhi + Ahi*Blo + Alo*Bhi  in the fp32 TMEM accumulator -- error ~2^-21.
+//
+// Structure of one CTA (256 threads, one 128 x BN output tile, BN = 64 | 128):
+//   * all 8 warps load the next k-block (32 fp32 = one 128-byte swizzle row per tile row) of A and B from
+//     global memory into registers, apply the optional fused BN+ReLU operand prologue, split hi/lo and
+//     store into shared memory in the canonical UMMA SWIZZLE_128B layout (K-major or MN-major, so the
+//     transposed operands of NN / TN need no transposition pass);
+//   * one thread issues 12 tcgen05.mma.kind::tf32 (4 k-steps x 3 split products) per k-block and commits
+//     them to the stage's mbarrier; the tensor core runs asynchronously while the next k-block is loaded
+//     (double-buffered shared memory);
+//   * epilogue: tcgen05.ld TMEM -> registers -> padded shared tile -> coalesced stores (+bias, +accumulate),
+//     optional per-tile column sum / sum-of-squares partials (BatchNorm statistics without re-reading z).
+#include <cstdlib>
+#include <type_traits>
+#include "common.cuh"
+
+namespace yolat {
+namespace tc {
+
+constexpr int BM = 128;        // output rows per CTA = TMEM lanes
+constexpr int BK = 32;         // fp32 per k-block = 128 bytes = one swizzle row
+constexpr int THREADS = 256;
+constexpr int STAGES = 2;
+constexpr uint32_t A_BYTES = BM * 128;
+
+struct Params {
+  const float* A; int64_t lda;
+  const float* B; int64_t ldb;
+  float* C; int64_t ldc;
+  int M, N; int64_t K;
+  const float* bias;
+  const float* a_sc; const float* a_sh;
+  const float* b_sc; const float* b_sh;
+  int accumulate;
+  int64_t k_chunk;       // reduction length per split (multiple of BK)
+  float* part;           // split-K partial tiles [splits][M][N] (null when gridDim.z == 1)
+  float* stat_part;      // [gridDim.y][2][N] column sum / sumsq of the stored tile (null = off)
+  int a_vec, b_vec;      // 16-byte vector loads are legal for A / B
+  int c_vec;             // 16-byte vector stores are legal for C
+};
+
+// ---- PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a descriptor / protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+  if (mbar_try_wait(addr, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(addr, parity)) {
+    if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, sm_100 version field = 1
+// (bit layout: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version [46,48) | layout [61,64)).
+constexpr uint32_t LAYOUT_SW128 = 2;          // K-major operands
+constexpr uint32_t LAYOUT_SW128_BASE32B = 1;  // MN-major 32-bit operands
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// Instruction descriptor for kind::tf32, fp32 accumulate
+// (c_format [4,6)=1 F32 | a_format [7,10)=2 TF32 | b_format [10,13)=2 | a_major 15 | b_major 16 | N>>3 [17,23) | M>>4 [24,29)).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  lo = x - hi;
+}
+__device__ __forceinline__ void store_split(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, const float4& v) {
+  float4 h, l;
+  split_tf32(v.x, h.x, l.x);
+  split_tf32(v.y, h.y, l.y);
+  split_tf32(v.z, h.z, l.z);
+  split_tf32(v.w, h.w, l.w);
+  *reinterpret_cast<float4*>(hi_base + off) = h;
+  *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+
+// ---- operand loaders -------------------------------------------------------------------------------
+// K-major operand: element (row, k) at base[row*ld + k].  ROWS x 32 tile = ROWS*8 16-byte chunks;
+// thread t owns chunk c = t&7 of rows (t>>3) + 32*i.
+template <int ROWS>
+struct KMajor {
+  static constexpr int PER_THREAD = ROWS / 32;
+  float4 v[PER_THREAD];
+  __device__ __forceinline__ void fetch(const float* __restrict__ base, int64_t ld, int row0, int rows_total, int64_t k0,
+                                        int64_t k_end, int vec, const float* __restrict__ sc,
+                                        const float* __restrict__ sh) {
+    const int t = threadIdx.x, c = t & 7;
+    const int64_t k = k0 + c * 4;
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; ++i) {
+      const int row = row0 + (t >> 3) + 32 * i;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows_total && k < k_end) {
+        const float* p = base + (int64_t)row * ld + k;
+        if (vec && k + 3 < k_end) {
+          x = __ldg(reinterpret_cast<const float4*>(p));
+        } else {
+          x.x = __ldg(p);
+          if (k + 1 < k_end) x.y = __ldg(p + 1);
+          if (k + 2 < k_end) x.z = __ldg(p + 2);
+          if (k + 3 < k_end) x.w = __ldg(p + 3);
+        }
+        if (sc) {   // fused BatchNorm + ReLU on the operand, per reduction index k
+          x.x = fmaxf(fmaf(x.x, __ldg(sc + k), __ldg(sh + k)), 0.f);
+          x.y = (k + 1 < k_end) ? fmaxf(fmaf(x.y, __ldg(sc + k + 1), __ldg(sh + k + 1)), 0.f) : 0.f;
+          x.z = (k + 2 < k_end) ? fmaxf(fmaf(x.z, __ldg(sc + k + 2), __ldg(sh + k + 2)), 0.f) : 0.f;
+          x.w = (k + 3 < k_end) ? fmaxf(fmaf(x.w, __ldg(sc + k + 3), __ldg(sh + k + 3)), 0.f) : 0.f;
+        }
+      }
+      v[i] = x;
+    }
+  }
+  __device__ __forceinline__ void stash(uint8_t* hi, uint8_t* lo) const {
+    const int t = threadIdx.x, c = t & 7;
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; ++i) {
+      const int row = (t >> 3) + 32 * i;
+      const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+      store_split(hi, lo, off, v[i]);
+    }
+  }
+};
+
+// MN-major operand: element (mn, k) at base[k*ld + mn].  MN x 32 tile; one 128-byte smem row holds 32
+// consecutive mn at one k; thread t owns chunk cm = t % (MN/4) of k-rows t/(MN/4) + (1024/MN)*i.
+template <int MN>
+struct MNMajor {
+  static constexpr int CPR = MN / 4;                 // 16-byte chunks per k-row
+  static constexpr int KR_PER_PASS = THREADS / CPR;  // k-rows covered per pass
+  static constexpr int PER_THREAD = BK / KR_PER_PASS;
+  float4 v[PER_THREAD];
+  __device__ __forceinline__ void fetch(const float* __restrict__ base, int64_t ld, int mn0, int mn_total, int64_t k0,
+                                        int64_t k_end, int vec, const float* __restrict__ sc,
+                                        const float* __restrict__ sh) {
+    const int t = threadIdx.x, cm = t % CPR;
+    const int mn = mn0 + cm * 4;
+    float4 s = make_float4(1.f, 1.f, 1.f, 1.f), h = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sc && mn < mn_total) {
+      s.x = __ldg(sc + mn); h.x = __ldg(sh + mn);
+      if (mn + 1 < mn_total) { s.y = __ldg(sc + mn + 1); h.y = __ldg(sh + mn + 1); }
+      if (mn + 2 < mn_total) { s.z = __ldg(sc + mn + 2); h.z = __ldg(sh + mn + 2); }
+      if (mn + 3 < mn_total) { s.w = __ldg(sc + mn + 3); h.w = __ldg(sh + mn + 3); }
+    }
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; ++i) {
+      const int64_t k = k0 + t / CPR + KR_PER_PASS * i;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < k_end && mn < mn_total) {
+        const float* p = base + k * ld + mn;
+        if (vec && mn + 3 < mn_total) {
+          x = __ldg(reinterpret_cast<const float4*>(p));
+        } else {
+          x.x = __ldg(p);
+          if (mn + 1 < mn_total) x.y = __ldg(p + 1);
+          if (mn + 2 < mn_total) x.z = __ldg(p + 2);
+          if (mn + 3 < mn_total) x.w = __ldg(p + 3);
+        }
+        if (sc) {   // fused BatchNorm + ReLU on the operand, per output index mn
+          x.x = fmaxf(fmaf(x.x, s.x, h.x), 0.f);
+          x.y = (mn + 1 < mn_total) ? fmaxf(fmaf(x.y, s.y, h.y), 0.f) : 0.f;
+          x.z = (mn + 2 < mn_total) ? fmaxf(fmaf(x.z, s.z, h.z), 0.f) : 0.f;
+          x.w = (mn + 3 < mn_total) ? fmaxf(fmaf(x.w, s.w, h.w), 0.f) : 0.f;
+        }
+      }
+      v[i] = x;
+    }
+  }
+  // 32-bit MN-major operands only exist in the SWIZZLE_128B_BASE32B layout: atoms of 32 mn x 4 k (4 rows of 128
+  // bytes), the 32-byte chunk index of a row XORed with the row index (Swizzle<2,5,2> on byte addresses).
+  // Tile = [k_atom (8)][mn_atom (MN/32)][4 k-rows][128 B]  =>  LBO = 512 B, SBO = MN/32 * 512 B.
+  __device__ __forceinline__ void stash(uint8_t* hi, uint8_t* lo) const {
+    const int t = threadIdx.x, cm = t % CPR;
+    const int c16 = cm & 7;
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; ++i) {
+      const int kr = t / CPR + KR_PER_PASS * i;
+      const int kr4 = kr & 3;
+      const uint32_t off = (uint32_t)(kr >> 2) * (uint32_t)(MN / 32 * 512) + (uint32_t)(cm >> 3) * 512u +
+                           (uint32_t)kr4 * 128u + (uint32_t)((((c16 >> 1) ^ kr4) << 5) | ((c16 & 1) << 4));
+      store_split(hi, lo, off, v[i]);
+    }
+  }
+};
+
+template <int MODE, int BN>
+struct Loaders {
+  using ALoad = typename std::conditional<MODE == GEMM_TN, MNMajor<BM>, KMajor<BM>>::type;
+  using BLoad = typename std::conditional<MODE == GEMM_NT, KMajor<BN>, MNMajor<BN>>::type;
+};
+
+// ---- the kernel ------------------------------------------------------------------------------------
+template <int MODE, int BN>
+__global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const Params p) {
+  constexpr uint32_t B_BYTES = BN * 128;
+  constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr bool A_MN = (MODE == GEMM_TN);
+  constexpr bool B_MN = (MODE != GEMM_NT);
+  constexpr uint32_t IDESC = make_idesc(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  constexpr int LDS = BN + 4;   // padded epilogue tile row (floats)
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t mbar_empty[STAGES];
+  __shared__ uint64_t mbar_done;
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_u32 + 1023u) & ~1023u) - raw_u32;
+  uint8_t* tiles = smem_raw + pad;            // 1024-byte aligned (SWIZZLE_128B atoms)
+  const uint32_t tiles_u32 = raw_u32 + pad;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int64_t k_begin = (int64_t)blockIdx.z * p.k_chunk;
+  const int64_t k_end = min(p.K, k_begin + p.k_chunk);
+  const int nkb = (int)((k_end - k_begin + BK - 1) / BK);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(&mbar_empty[s]), 1);
+    mbar_init(smem_u32(&mbar_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_slot;
+
+  typename Loaders<MODE, BN>::ALoad la;
+  typename Loaders<MODE, BN>::BLoad lb;
+  auto fetch = [&](int kb) {
+    const int64_t k0 = k_begin + (int64_t)kb * BK;
+    la.fetch(p.A, p.lda, m0, p.M, k0, k_end, p.a_vec, p.a_sc, p.a_sh);
+    lb.fetch(p.B, p.ldb, n0, p.N, k0, k_end, p.b_vec, MODE == GEMM_TN ? p.b_sc : nullptr, p.b_sh);
+  };
+
+  if (nkb > 0) fetch(0);
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb % STAGES;
+    const int use = kb / STAGES;
+    if (use > 0) mbar_wait(smem_u32(&mbar_empty[s]), (uint32_t)((use - 1) & 1));   // MMAs that read stage s are done
+    uint8_t* st = tiles + (uint32_t)s * STAGE_BYTES;
+    la.stash(st, st + A_BYTES);
+    lb.stash(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES);
+    if (kb + 1 < nkb) fetch(kb + 1);          // global loads of the next k-block fly during sync + MMA issue
+    fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t sa = tiles_u32 + (uint32_t)s * STAGE_BYTES;
+      const uint32_t sb = sa + 2 * A_BYTES;
+#pragma unroll
+      for (int ks = 0; ks < BK / 8; ++ks) {
+        const uint32_t a_off = A_MN ? (uint32_t)ks * (BM / 32 * 1024) : (uint32_t)ks * 32u;
+        const uint32_t b_off = B_MN ? (uint32_t)ks * (BN / 32 * 1024) : (uint32_t)ks * 32u;
+        const uint64_t a_hi = A_MN ? make_desc(sa + a_off, 512, BM / 32 * 512, LAYOUT_SW128_BASE32B)
+                                   : make_desc(sa + a_off, 16, 1024, LAYOUT_SW128);
+        const uint64_t a_lo = A_MN ? make_desc(sa + A_BYTES + a_off, 512, BM / 32 * 512, LAYOUT_SW128_BASE32B)
+                                   : make_desc(sa + A_BYTES + a_off, 16, 1024, LAYOUT_SW128);
+        const uint64_t b_hi = B_MN ? make_desc(sb + b_off, 512, BN / 32 * 512, LAYOUT_SW128_BASE32B)
+                                   : make_desc(sb + b_off, 16, 1024, LAYOUT_SW128);
+        const uint64_t b_lo = B_MN ? make_desc(sb + B_BYTES + b_off, 512, BN / 32 * 512, LAYOUT_SW128_BASE32B)
+                                   : make_desc(sb + B_BYTES + b_off, 16, 1024, LAYOUT_SW128);
+        umma_tf32(tmem_d, a_lo, b_hi, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
+        umma_tf32(tmem_d, a_hi, b_lo, IDESC, 1u);
+        umma_tf32(tmem_d, a_hi, b_hi, IDESC, 1u);
+      }
+      umma_commit(smem_u32(&mbar_empty[s]));
+      if (kb + 1 == nkb) umma_commit(smem_u32(&mbar_done));
+    }
+  }
+
+  // ---- epilogue ----------------------------------------------------------------------------------
+  float* cs = reinterpret_cast<float*>(tiles);   // [BM][LDS], aliases the (now idle) operand stages
+  if (nkb > 0) {
+    mbar_wait(smem_u32(&mbar_done), 0u);
+    tc_fence_after();
+    const int q = warp & 3, h = warp >> 2;       // TMEM lane quarter / column half of this warp
+    const int r = q * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < BN / 64; ++j) {
+      float v[32];
+      const int col = h * (BN / 2) + j * 32;
+      tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
+      float* dst = cs + r * LDS + col;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  } else {
+    for (int i = tid; i < BM * LDS; i += THREADS) cs[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+
+  const bool split = gridDim.z > 1;
+  const int rows = min(BM, p.M - m0), cols = min(BN, p.N - n0);
+  if (split) {
+    float* dst = p.part + ((int64_t)blockIdx.z * p.M + m0) * p.N + n0;
+    for (int idx = tid; idx < BM * (BN / 4); idx += THREADS) {
+      const int rr = idx / (BN / 4), c4 = (idx % (BN / 4)) * 4;
+      if (rr >= rows) continue;
+      const float4 v = *reinterpret_cast<const float4*>(cs + rr * LDS + c4);
+      float* o = dst + (int64_t)rr * p.N + c4;
+      if ((p.N & 3) == 0 && c4 + 3 < cols) {
+        *reinterpret_cast<float4*>(o) = v;
+      } else {
+        if (c4 < cols) o[0] = v.x;
+        if (c4 + 1 < cols) o[1] = v.y;
+        if (c4 + 2 < cols) o[2] = v.z;
+        if (c4 + 3 < cols) o[3] = v.w;
+      }
+    }
+  } else {
+    for (int idx = tid; idx < BM * (BN / 4); idx += THREADS) {
+      const int rr = idx / (BN / 4), c4 = (idx % (BN / 4)) * 4;
+      if (rr >= rows || c4 >= cols) continue;
+      float4 v = *reinterpret_cast<const float4*>(cs + rr * LDS + c4);
+      if (p.bias) {
+        v.x += __ldg(p.bias + n0 + c4);
+        if (c4 + 1 < cols) v.y += __ldg(p.bias + n0 + c4 + 1);
+        if (c4 + 2 < cols) v.z += __ldg(p.bias + n0 + c4 + 2);
+        if (c4 + 3 < cols) v.w += __ldg(p.bias + n0 + c4 + 3);
+      }
+      float* o = p.C + (int64_t)(m0 + rr) * p.ldc + n0 + c4;
+      if (p.c_vec && c4 + 3 < cols) {
+        if (p.accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(o);
+          v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+        }
+        *reinterpret_cast<float4*>(o) = v;
+      } else {
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c4 + e < cols) o[e] = p.accumulate ? o[e] + vv[e] : vv[e];
+      }
+    }
+    if (p.stat_part && tid < BN) {   // column statistics of z = acc + bias over this tile's valid rows
+      const int c = tid;
+      if (c < cols) {
+        const float b = p.bias ? __ldg(p.bias + n0 + c) : 0.f;
+        float s = 0.f, ss = 0.f;
+        for (int rr = 0; rr < rows; ++rr) {
+          const float z = cs[rr * LDS + c] + b;
+          s += z;
+          ss = fmaf(z, z, ss);
+        }
+        p.stat_part[((int64_t)blockIdx.y * 2 + 0) * p.N + n0 + c] = s;
+        p.stat_part[((int64_t)blockIdx.y * 2 + 1) * p.N + n0 + c] = ss;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, BN);
+}
+
+template <int MODE, int BN>
+static cudaError_t launch(const Params& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (2 * A_BYTES + 2 * BN * 128) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  k_tc_gemm<MODE, BN><<<grid, THREADS, smem, st>>>(p);
+  return cudaSuccess;
+}
+
+}  // namespace tc
+
+__global__ void k_splitk_sum(const float* __restrict__ part, int ksplit, int M, int N,
+                                      const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int accumulate);
+
+static bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Planning shared by the dry (workspace query) and the real call.
+struct TcPlan { int bn, gm, gn, ksplit; int64_t k_chunk; };
+static TcPlan tc_plan(int M, int N, int64_t K, GemmMode mode) {
+  TcPlan pl;
+  pl.bn = N > 64 ? 128 : 64;
+  pl.gm = (int)cdiv(M, tc::BM);
+  pl.gn = (int)cdiv(N, pl.bn);
+  const int64_t tiles = (int64_t)pl.gm * pl.gn;
+  const int64_t nkb = cdiv(K > 0 ? K : 1, tc::BK);
+  int64_t want = 1;
+  if (tiles < kNumSMs) want = cdiv(2 * kNumSMs, tiles);
+  // the fp32 TMEM accumulator is rounded once per MMA: keep every split's reduction short so the
+  // rounding stays far below the 1e-4 parity bar on the long row reductions of dW = dy^T x.
+  const int64_t max_chunk_kb = (mode == GEMM_TN) ? 64 : 128;
+  if (cdiv(nkb, want) > max_chunk_kb) want = cdiv(nkb, max_chunk_kb);
+  const int64_t cap = nkb / 2 > 0 ? nkb / 2 : 1;   // at least 2 k-blocks per split
+  if (want > cap) want = cap;
+  if (want > 1024) want = 1024;
+  if (want < 1) want = 1;
+  pl.k_chunk = align_up(cdiv(K > 0 ? K : 1, want), tc::BK);
+  pl.ksplit = (int)cdiv(K > 0 ? K : 1, pl.k_chunk);
+  return pl;
+}
+
+static int gemm_tc(const GemmArgs& a, GemmMode mode, Arena& ws, float* stat_part, int* stat_nparts, cudaStream_t st) {
+  const TcPlan pl = tc_plan(a.M, a.N, a.K, mode);
+  float* part = nullptr;
+  if (pl.ksplit > 1) part = ws.take((int64_t)pl.ksplit * a.M * a.N);
+  if (stat_nparts) *stat_nparts = pl.ksplit > 1 ? 0 : pl.gm;
+  if (ws.dry()) return YOLAT_OK;
+  if (ws.overflow) return YOLAT_ERR_WORKSPACE;
+  tc::Params p{};
+  p.A = a.A; p.lda = a.lda; p.B = a.B; p.ldb = a.ldb; p.C = a.C; p.ldc = a.ldc;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias;
+  p.a_sc = a.a_sc; p.a_sh = a.a_sh; p.b_sc = a.b_sc; p.b_sh = a.b_sh;
+  p.accumulate = a.accumulate;
+  p.k_chunk = pl.k_chunk;
+  p.part = part;
+  p.stat_part = pl.ksplit > 1 ? nullptr : stat_part;
+  p.a_vec = aligned16p(a.A) && (a.lda % 4 == 0);
+  p.b_vec = aligned16p(a.B) && (a.ldb % 4 == 0);
+  p.c_vec = aligned16p(a.C) && (a.ldc % 4 == 0);
+  dim3 grid(pl.gn, pl.gm, pl.ksplit);
+  cudaError_t e = cudaSuccess;
+#define YOLAT_TC_CASE(MODE_)                                                    \
+  case MODE_:                                                                   \
+    e = pl.bn == 128 ? tc::launch<MODE_, 128>(p, grid, st) : tc::launch<MODE_, 64>(p, grid, st); \
+    break;
+  switch (mode) {
+    YOLAT_TC_CASE(GEMM_NT)
+    YOLAT_TC_CASE(GEMM_NN)
+    YOLAT_TC_CASE(GEMM_TN)
+  }
+#undef YOLAT_TC_CASE
+  if (e != cudaSuccess) { set_last_error(e); return YOLAT_ERR_LAUNCH; }
+  YOLAT_CHECK_LAUNCH();
+  if (pl.ksplit > 1) {
+    const int64_t tot = (int64_t)a.M * a.N;
+    k_splitk_sum<<<(unsigned)cdiv(tot, 256), 256, 0, st>>>(part, pl.ksplit, a.M, a.N, a.bias, a.C, a.ldc,
+                                                                    a.accumulate);
+    YOLAT_CHECK_LAUNCH();
+  }
+  return YOLAT_OK;
+}
+
+// C = sum_z part[z] (+ bias), fixed summation order (deterministic)
+__global__ void k_splitk_sum(const float* __restrict__ part, int ksplit, int M, int N,
+                                      const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int accumulate) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)M * N) return;
+  const int m = (int)(idx / N), n = (int)(idx % N);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int z = 0;
+  const int64_t stride = (int64_t)M * N;
+  for (; z + 3 < ksplit; z += 4) {
+    s0 += part[(int64_t)z * stride + idx];
+    s1 += part[(int64_t)(z + 1) * stride + idx];
+    s2 += part[(int64_t)(z + 2) * stride + idx];
+    s3 += part[(int64_t)(z + 3) * stride + idx];
+  }
+  for (; z < ksplit; ++z) s0 += part[(int64_t)z * stride + idx];
+  float s = (s0 + s1) + (s2 + s3);
+  if (bias) s += bias[n];
+  float* c = C + (int64_t)m * ldc + n;
+  *c = accumulate ? (*c + s) : s;
+}
+
+static bool gemm_use_tc();
+
+int gemm_stats(const GemmArgs& a, GemmMode mode, Arena& ws, float** stat_part, int* nparts, cudaStream_t st) {
+  if (a.M <= 0 || a.N <= 0) { if (nparts) *nparts = 0; return YOLAT_OK; }
+  if (!gemm_use_tc()) {
+    if (nparts) *nparts = 0;
+    return gemm_simt(a, mode, ws, st);
+  }
+  float* sp = nullptr;
+  if (stat_part) {
+    sp = ws.take((int64_t)cdiv(a.M, tc::BM) * 2 * a.N);
+    *stat_part = sp;
+  }
+  return gemm_tc(a, mode, ws, sp, nparts, st);
+}
+
+int gemm(const GemmArgs& a, GemmMode mode, Arena& ws, cudaStream_t st) {
+  return gemm_stats(a, mode, ws, nullptr, nullptr, st);
+}
+
+static bool gemm_use_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YOLAT_GEMM");
+    v = (e && e[0] == 's') ? 0 : 1;   // YOLAT_GEMM=simt selects the exact-fp32 SIMT kernel (debugging aid)
+  }
+  return v == 1;
+}
+
+}  // namespace yolat

@@ -25,12 +25,14 @@ int mlp_fwd_impl(const float* x, int64_t ldx, int64_t M, int K, const float* w, 
   GemmArgs a{};
   a.A = x; a.lda = ldx; a.B = w; a.ldb = K; a.M = (int)M; a.N = Nout; a.K = K; a.bias = b;
   if (t.z || (dry && (has_bn || has_relu))) { a.C = t.z; a.ldc = Nout; } else { a.C = y; a.ldc = ldy; }
-  YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
   if (has_bn) {
     yolat_bn bb = dry ? yolat_bn{} : *bn;
-    YOLAT_TRY(bn_forward_stats(t.z, Nout, M, Nout, &bb, training, t.stat, ws, st));
+    YOLAT_TRY(linear_bn_stats(a, ws, &bb, training, t.stat, st));
     if (!dry) YOLAT_TRY(bn_apply(t.z, Nout, M, Nout, t.stat, has_relu, y, ldy, st));
-  } else if (has_relu && !dry) {
+  } else {
+    YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
+  }
+  if (!has_bn && has_relu && !dry) {
     // identity "statistics": sc = 1, sh = 0 are not materialised; copy + relu
     YOLAT_TRY(relu_bwd(t.z, Nout, t.z, Nout, M, Nout, y, ldy, st));   // y = z > 0 ? z : 0
   }
@@ -84,6 +86,27 @@ int mlp_bwd_impl(const float* x, int64_t ldx, int64_t M, int K, const float* w, 
 using namespace yolat;
 
 extern "C" {
+
+int64_t yolat_gemm_ws_floats(int mode, int64_t M, int64_t N, int64_t K) {
+  if (mode < 0 || mode > 2) return -1;
+  Arena ws(nullptr, 0);
+  GemmArgs a{};
+  a.M = (int)M; a.N = (int)N; a.K = K;
+  gemm(a, (GemmMode)mode, ws, nullptr);
+  return ws.off;
+}
+
+int yolat_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
+               int64_t N, int64_t K, const float* bias, int accumulate, float* ws, int64_t ws_floats, void* stream) {
+  if (mode < 0 || mode > 2 || !C || M < 0 || N < 0 || K < 0 || (K > 0 && (!A || !B))) return YOLAT_ERR_INVALID;
+  if (M >= (1ll << 31) || N >= (1ll << 31)) return YOLAT_ERR_UNSUPPORTED;
+  static float dummy;
+  Arena wsa(ws ? ws : &dummy, ws ? ws_floats : 0);
+  GemmArgs a{};
+  a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc;
+  a.M = (int)M; a.N = (int)N; a.K = K; a.bias = bias; a.accumulate = accumulate;
+  return gemm(a, (GemmMode)mode, wsa, (cudaStream_t)stream);
+}
 
 int64_t yolat_mlp_tape_floats(int64_t M, int K, int Nout, int flags) {
   (void)K;

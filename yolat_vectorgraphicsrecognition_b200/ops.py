@@ -303,3 +303,30 @@ class SoftmaxXentFn(torch.autograd.Function):
 
 def softmax_cross_entropy(logits, labels):
     return SoftmaxXentFn.apply(logits, labels)
+
+
+# --------------------------------------------------------------------------------------------------
+# raw dense product on the tensor cores (the block under every nn.Linear; no autograd)
+# --------------------------------------------------------------------------------------------------
+GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+
+
+def gemm(mode, a, b, bias=None, out=None, accumulate=False):
+    """mode NT: a[M,K] @ b[N,K]^T;  NN: a[M,K] @ b[K,N];  TN: a[K,M]^T @ b[K,N]  (+ bias[N]); fp32, row-major,
+    arbitrary row strides."""
+    L.require_cuda(a, b)
+    lib = L.lib()
+    if a.dtype != torch.float32 or b.dtype != torch.float32 or a.stride(1) != 1 or b.stride(1) != 1:
+        raise ValueError('gemm operands must be fp32 with unit inner stride')
+    if mode == GEMM_NT:
+        (M, K), N = a.shape, b.shape[0]
+    elif mode == GEMM_NN:
+        (M, K), N = a.shape, b.shape[1]
+    else:
+        (K, M), N = a.shape, b.shape[1]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    ws = L.workspace.get(lib.yolat_gemm_ws_floats(mode, M, N, K), a.device)
+    L.check(lib.yolat_gemm(mode, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0),
+                           M, N, K, L.ptr(bias), int(accumulate), ws.data_ptr(), ws.numel(), L.stream()), 'gemm')
+    return out
