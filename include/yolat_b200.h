@@ -98,7 +98,12 @@ int64_t yolat_gp2_bwd_ws_floats(int64_t N, int64_t E, int Cin, int Cn, int C);
 
 /* forward (torch_vertex.py:319-337).  x [N,Cin], x_node [N,Cn], attr [E,4] in ORIGINAL edge order,
  * edge_weight [E] or NULL (`norm`, :337).  out [N,C] = mean-aggregated messages + lin_r(x);
- * xnode_out [N,C] = mlp_node(x_node).  training != 0: batch statistics + running-stat update. */
+ * xnode_out [N,C] = mlp_node(x_node).
+ * training: bit 0 (YOLAT_GP2_TRAINING) = batch statistics + running-stat update; bit 1 (YOLAT_GP2_NO_TAPE) =
+ * forward only -- the per-edge activations z1 / z2 are not written to the tape (no [E,C] tensor reaches HBM)
+ * and yolat_gp2_bwd must not be called on that tape. */
+#define YOLAT_GP2_TRAINING 1
+#define YOLAT_GP2_NO_TAPE 2
 int yolat_gp2_fwd(const yolat_gp2_params* p, int Cin, int Cn, int C,
                   const float* x, int64_t ldx, const float* x_node, int64_t ldxn,
                   const float* attr, const float* edge_weight,

@@ -10,7 +10,7 @@ namespace yolat {
 
 constexpr int ST_COLS = 32;   // columns per CTA (one warp-width => 128-byte coalesced row segments)
 constexpr int ST_ROWS = 8;    // row lanes per CTA
-constexpr int ST_ROWS_PER_CTA = 1024;
+constexpr int ST_ROWS_PER_CTA = 256;   // short per-CTA row loops: these reductions are latency-bound, not bandwidth-bound
 
 // part layout: [nparts][2][C]
 __global__ void __launch_bounds__(ST_COLS* ST_ROWS) k_colstats(const float* __restrict__ z, int64_t ldz, int64_t M, int C,
@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(ST_COLS* ST_ROWS) k_colstats(const float* __re
   const int64_t r1 = min(M, r0 + ST_ROWS_PER_CTA);
   float a = 0.f, b = 0.f;
   if (c < C) {
+#pragma unroll 8
     for (int64_t r = r0 + ty; r < r1; r += ST_ROWS) {
       float v = z[r * ldz + c];
       a += v;
@@ -45,10 +46,22 @@ __device__ __forceinline__ void reduce_parts2(const float* __restrict__ part, in
   const int tx = threadIdx.x, ty = threadIdx.y;
   double a = 0.0, b = 0.0;
   if (c < C) {
-    for (int p = ty; p < nparts; p += 32) {
+    double a1 = 0.0, b1 = 0.0, a2 = 0.0, b2 = 0.0, a3 = 0.0, b3 = 0.0;
+    int p = ty;
+    for (; p + 96 < nparts; p += 128) {     // 8 independent loads in flight per thread
+      const float x0 = part[((int64_t)p * 2 + 0) * C + c], y0 = part[((int64_t)p * 2 + 1) * C + c];
+      const float x1 = part[((int64_t)(p + 32) * 2 + 0) * C + c], y1 = part[((int64_t)(p + 32) * 2 + 1) * C + c];
+      const float x2 = part[((int64_t)(p + 64) * 2 + 0) * C + c], y2 = part[((int64_t)(p + 64) * 2 + 1) * C + c];
+      const float x3 = part[((int64_t)(p + 96) * 2 + 0) * C + c], y3 = part[((int64_t)(p + 96) * 2 + 1) * C + c];
+      a += (double)x0; b += (double)y0; a1 += (double)x1; b1 += (double)y1;
+      a2 += (double)x2; b2 += (double)y2; a3 += (double)x3; b3 += (double)y3;
+    }
+    for (; p < nparts; p += 32) {
       a += (double)part[((int64_t)p * 2 + 0) * C + c];
       b += (double)part[((int64_t)p * 2 + 1) * C + c];
     }
+    a = (a + a1) + (a2 + a3);
+    b = (b + b1) + (b2 + b3);
   }
   sm[0][ty][tx] = a; sm[1][ty][tx] = b;
   __syncthreads();
@@ -168,6 +181,7 @@ __global__ void __launch_bounds__(ST_COLS* ST_ROWS) k_bn_bwd_partial(BnBwdArgs a
   float p = 0.f, q = 0.f;
   if (c < a.C) {
     const float sc = a.stat[c], sh = a.stat[a.C + c], mean = a.stat[2 * a.C + c], invstd = a.stat[3 * a.C + c];
+#pragma unroll 8
     for (int64_t r = r0 + ty; r < r1; r += ST_ROWS) {
       const float zz = a.z[r * a.ldz + c];
       float dy = bwd_load_dy(a, r, c);
@@ -257,8 +271,10 @@ __global__ void __launch_bounds__(ST_COLS* ST_ROWS) k_colsum_partial(const float
   const int64_t r0 = (int64_t)blockIdx.y * ST_ROWS_PER_CTA;
   const int64_t r1 = min(M, r0 + ST_ROWS_PER_CTA);
   float a = 0.f;
-  if (c < C)
+  if (c < C) {
+#pragma unroll 8
     for (int64_t r = r0 + ty; r < r1; r += ST_ROWS) a += z[r * ldz + c];
+  }
   s1[ty][tx] = a;
   __syncthreads();
   if (ty == 0 && c < C) {

@@ -222,6 +222,14 @@ int edge_agg(const GraphView& g, int64_t N, int C, const float* z2, const float*
 int edge_bwd_scatter(const GraphView& g, int64_t N, int C, const float* dz1, const float* attr, float* dpq,
                      float* part, float* dw1c, cudaStream_t st);
 
+// edge_fused.cu: the fused gather -> edge MLP (tcgen05) -> statistics / segmented mean kernel (C == 64)
+enum { EF_TAPE = 1, EF_STATS = 2, EF_AGG = 4 };
+bool edge_fused_supported(int C);
+int edge_fused_grid(int64_t E);
+int edge_fused(const GraphView& g, int64_t N, int64_t E, int flags, const float* pq, const float* attr, const float* w1,
+               int Cin, const float* b1, const float* stat1, const float* w2, const float* b2, const float* stat2,
+               const float* ew, float* z1, float* z2, float* part, float* out, int64_t ldo, cudaStream_t st);
+
 int colsum(const float* a, int64_t lda, int64_t M, int C, float* out, Arena& ws, cudaStream_t st);
 int fill_zero(float* p, int64_t n, cudaStream_t st);
 

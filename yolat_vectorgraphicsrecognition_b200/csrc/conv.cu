@@ -12,6 +12,7 @@
 //   out += mean_i relu(bn2(z2))                   k_edge_agg (segmented, no atomics)
 //   xn   = relu(bn_n(x_node Wn^T + bn))           GEMM + column stats + apply
 // Tape (saved for backward): z1, z2, zn and the three BN statistic blocks.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace yolat {
@@ -29,15 +30,27 @@ static void gp2_tape_layout(Arena& t, int64_t N, int64_t E, int C, Gp2Tape* o) {
   o->statn = t.take(4 * C);
 }
 
+// YOLAT_EDGE=unfused selects the three-kernel edge path (z1 -> GEMM -> aggregate) instead of edge_fused.cu
+static bool gemm_fused_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YOLAT_EDGE");
+    v = (e && e[0] == 'u') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool gp2_channels_ok(int Cin, int Cn, int C) {
   return (C == 32 || C == 64 || C == 128) && Cin >= 1 && Cn >= 1;
 }
 
 static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const float* x, int64_t ldx,
                         const float* x_node, int64_t ldxn, const float* attr, const float* ew,
-                        const int32_t* graph, int64_t N, int64_t E, int training, float* out, int64_t ldo,
+                        const int32_t* graph, int64_t N, int64_t E, int mode, float* out, int64_t ldo,
                         float* xnode_out, int64_t ldxo, Arena& tape, Arena& ws, cudaStream_t st) {
   const bool dry = ws.dry();
+  const int training = (mode & YOLAT_GP2_TRAINING) ? 1 : 0;
+  const bool no_tape = (mode & YOLAT_GP2_NO_TAPE) != 0;   // forward only: z1 / z2 are never written
   Gp2Tape t;
   gp2_tape_layout(tape, N, E, C, &t);
   float* wpq = ws.take((int64_t)2 * C * Cin);
@@ -65,19 +78,46 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
       a.M = (int)N; a.N = 2 * C; a.K = Cin;
       YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
     }
-    if (!dry) {
-      YOLAT_TRY(edge_z1(g, N, C, pq, attr, p->w1, Cin, p->b1, t.z1, training ? part1 : nullptr, st));
-      YOLAT_TRY(bn_finalize_from_partials(part1, nparts, E, C, &p->bn1, training, t.stat1, st));
+    if (edge_fused_supported(C) && gemm_fused_enabled()) {
+      // K-EDGE fused path (edge_fused.cu): pass A = BN1 statistics (no [E,C] store), then the tcgen05 kernel
+      // once for the BN2 statistics and once for the segmented mean; z1 / z2 reach HBM only as backward tape.
+      const int ngrid = edge_fused_grid(E);
+      float* part2 = ws.take((int64_t)ngrid * 2 * C);
+      if (!dry) {
+        if (ws.overflow) return YOLAT_ERR_WORKSPACE;
+        if (training) YOLAT_TRY(edge_z1(g, N, C, pq, attr, p->w1, Cin, p->b1, nullptr, part1, st));
+        YOLAT_TRY(bn_finalize_from_partials(part1, nparts, E, C, &p->bn1, training, t.stat1, st));
+        if (training) {
+          YOLAT_TRY(edge_fused(g, N, E, EF_STATS | (no_tape ? 0 : EF_TAPE), pq, attr, p->w1, Cin, p->b1, t.stat1, p->w2,
+                               p->b2, nullptr, ew, t.z1, t.z2, part2, nullptr, 0, st));
+          YOLAT_TRY(bn_finalize_from_partials(part2, ngrid, E, C, &p->bn2, 1, t.stat2, st));
+          if (no_tape) {
+            YOLAT_TRY(edge_fused(g, N, E, EF_AGG, pq, attr, p->w1, Cin, p->b1, t.stat1, p->w2, p->b2, t.stat2, ew,
+                                 nullptr, nullptr, nullptr, out, ldo, st));
+          } else {
+            YOLAT_TRY(edge_agg(g, N, C, t.z2, t.stat2, ew, out, ldo, st));
+          }
+        } else {
+          YOLAT_TRY(bn_finalize_from_partials(nullptr, 0, E, C, &p->bn2, 0, t.stat2, st));
+          YOLAT_TRY(edge_fused(g, N, E, EF_AGG | (no_tape ? 0 : EF_TAPE), pq, attr, p->w1, Cin, p->b1, t.stat1, p->w2,
+                               p->b2, t.stat2, ew, t.z1, t.z2, nullptr, out, ldo, st));
+        }
+      }
+    } else {
+      if (!dry) {
+        YOLAT_TRY(edge_z1(g, N, C, pq, attr, p->w1, Cin, p->b1, t.z1, training ? part1 : nullptr, st));
+        YOLAT_TRY(bn_finalize_from_partials(part1, nparts, E, C, &p->bn1, training, t.stat1, st));
+      }
+      {
+        GemmArgs a{};
+        a.A = t.z1; a.lda = C; a.B = dry ? nullptr : p->w2; a.ldb = C; a.C = t.z2; a.ldc = C;
+        a.M = (int)E; a.N = C; a.K = C; a.bias = dry ? nullptr : p->b2;
+        a.a_sc = t.stat1; a.a_sh = dry ? nullptr : t.stat1 + C;
+        yolat_bn bn2 = dry ? yolat_bn{} : p->bn2;
+        YOLAT_TRY(linear_bn_stats(a, ws, &bn2, training, t.stat2, st));
+      }
+      if (!dry) YOLAT_TRY(edge_agg(g, N, C, t.z2, t.stat2, ew, out, ldo, st));
     }
-    {
-      GemmArgs a{};
-      a.A = t.z1; a.lda = C; a.B = dry ? nullptr : p->w2; a.ldb = C; a.C = t.z2; a.ldc = C;
-      a.M = (int)E; a.N = C; a.K = C; a.bias = dry ? nullptr : p->b2;
-      a.a_sc = t.stat1; a.a_sh = dry ? nullptr : t.stat1 + C;
-      yolat_bn bn2 = dry ? yolat_bn{} : p->bn2;
-      YOLAT_TRY(linear_bn_stats(a, ws, &bn2, training, t.stat2, st));
-    }
-    if (!dry) YOLAT_TRY(edge_agg(g, N, C, t.z2, t.stat2, ew, out, ldo, st));
   }
   // ---- node path: mlp_node(x_node)  (torch_vertex.py:326) -----------------------------------------
   {

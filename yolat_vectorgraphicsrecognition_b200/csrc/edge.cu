@@ -104,7 +104,7 @@ k_edge_z1(GraphView g, int64_t N, const float* __restrict__ pq, const float* __r
         s[q] += v;
         ss[q] = fmaf(v, v, ss[q]);
       }
-      stv<CPL>(z1 + (int64_t)slot * C + c0, z);
+      if (z1) stv<CPL>(z1 + (int64_t)slot * C + c0, z);
     }
   }
   if (part == nullptr) return;

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace yolat {
 namespace tc {
@@ -46,107 +47,6 @@ struct Params {
   int a_vec, b_vec;      // 16-byte vector loads are legal for A / B
   int c_vec;             // 16-byte vector stores are legal for C
 };
-
-// ---- PTX helpers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(addr), "r"(parity)
-      : "memory");
-  return ok;
-}
-// Bounded wait: a descriptor / protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
-  if (mbar_try_wait(addr, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(addr, parity)) {
-    if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t mbar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Shared-memory matrix descriptor, sm_100 version field = 1
-// (bit layout: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version [46,48) | layout [61,64)).
-constexpr uint32_t LAYOUT_SW128 = 2;          // K-major operands
-constexpr uint32_t LAYOUT_SW128_BASE32B = 1;  // MN-major 32-bit operands
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout << 61;
-  return d;
-}
-// Instruction descriptor for kind::tf32, fp32 accumulate
-// (c_format [4,6)=1 F32 | a_format [7,10)=2 TF32 | b_format [10,13)=2 | a_major 15 | b_major 16 | N>>3 [17,23) | M>>4 [24,29)).
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  lo = x - hi;
-}
-__device__ __forceinline__ void store_split(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, const float4& v) {
-  float4 h, l;
-  split_tf32(v.x, h.x, l.x);
-  split_tf32(v.y, h.y, l.y);
-  split_tf32(v.z, h.z, l.z);
-  split_tf32(v.w, h.w, l.w);
-  *reinterpret_cast<float4*>(hi_base + off) = h;
-  *reinterpret_cast<float4*>(lo_base + off) = l;
-}
 
 // ---- operand loaders -------------------------------------------------------------------------------
 // K-major operand: element (row, k) at base[row*ld + k].  ROWS x 32 tile = ROWS*8 16-byte chunks;
@@ -300,23 +200,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const Params p) {
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_slot;
 
-  typename Loaders<MODE, BN>::ALoad la;
-  typename Loaders<MODE, BN>::BLoad lb;
-  auto fetch = [&](int kb) {
+  // Two k-blocks of global loads are kept in flight per thread (register sets 0/1 <-> smem stages 0/1):
+  // the loop is latency-bound on the loads, not on the tensor core.
+  typename Loaders<MODE, BN>::ALoad la[2];
+  typename Loaders<MODE, BN>::BLoad lb[2];
+  auto fetch = [&](int kb, typename Loaders<MODE, BN>::ALoad& ra, typename Loaders<MODE, BN>::BLoad& rb) {
     const int64_t k0 = k_begin + (int64_t)kb * BK;
-    la.fetch(p.A, p.lda, m0, p.M, k0, k_end, p.a_vec, p.a_sc, p.a_sh);
-    lb.fetch(p.B, p.ldb, n0, p.N, k0, k_end, p.b_vec, MODE == GEMM_TN ? p.b_sc : nullptr, p.b_sh);
+    ra.fetch(p.A, p.lda, m0, p.M, k0, k_end, p.a_vec, p.a_sc, p.a_sh);
+    rb.fetch(p.B, p.ldb, n0, p.N, k0, k_end, p.b_vec, MODE == GEMM_TN ? p.b_sc : nullptr, p.b_sh);
   };
-
-  if (nkb > 0) fetch(0);
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb % STAGES;
+  auto step = [&](int kb, int s, typename Loaders<MODE, BN>::ALoad& ra, typename Loaders<MODE, BN>::BLoad& rb) {
     const int use = kb / STAGES;
     if (use > 0) mbar_wait(smem_u32(&mbar_empty[s]), (uint32_t)((use - 1) & 1));   // MMAs that read stage s are done
     uint8_t* st = tiles + (uint32_t)s * STAGE_BYTES;
-    la.stash(st, st + A_BYTES);
-    lb.stash(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES);
-    if (kb + 1 < nkb) fetch(kb + 1);          // global loads of the next k-block fly during sync + MMA issue
+    ra.stash(st, st + A_BYTES);
+    rb.stash(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES);
+    if (kb + STAGES < nkb) fetch(kb + STAGES, ra, rb);
     fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the tensor core
     __syncthreads();
     if (tid == 0) {
@@ -342,6 +241,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const Params p) {
       umma_commit(smem_u32(&mbar_empty[s]));
       if (kb + 1 == nkb) umma_commit(smem_u32(&mbar_done));
     }
+  };
+
+  static_assert(STAGES == 2, "the main loop is unrolled by the stage count");
+  if (nkb > 0) fetch(0, la[0], lb[0]);
+  if (nkb > 1) fetch(1, la[1], lb[1]);
+  for (int kb = 0; kb < nkb; kb += 2) {
+    step(kb, 0, la[0], lb[0]);
+    if (kb + 1 < nkb) step(kb + 1, 1, la[1], lb[1]);
   }
 
   // ---- epilogue ----------------------------------------------------------------------------------
@@ -409,16 +316,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const Params p) {
           if (c4 + e < cols) o[e] = p.accumulate ? o[e] + vv[e] : vv[e];
       }
     }
-    if (p.stat_part && tid < BN) {   // column statistics of z = acc + bias over this tile's valid rows
-      const int c = tid;
-      if (c < cols) {
-        const float b = p.bias ? __ldg(p.bias + n0 + c) : 0.f;
-        float s = 0.f, ss = 0.f;
-        for (int rr = 0; rr < rows; ++rr) {
-          const float z = cs[rr * LDS + c] + b;
-          s += z;
-          ss = fmaf(z, z, ss);
-        }
+    if (p.stat_part) {   // column statistics of z = acc + bias over this tile's valid rows (block-uniform branch)
+      constexpr int GROUPS = THREADS / BN;          // row groups working on the same column
+      constexpr int RPG = BM / GROUPS;
+      __shared__ float red[2][THREADS];
+      const int c = tid % BN, g = tid / BN;
+      const float b = (p.bias && c < cols) ? __ldg(p.bias + n0 + c) : 0.f;
+      float s = 0.f, ss = 0.f;
+      const int r_end = min(rows, (g + 1) * RPG);
+#pragma unroll 8
+      for (int rr = g * RPG; rr < r_end; ++rr) {
+        const float z = cs[rr * LDS + c] + b;
+        s += z;
+        ss = fmaf(z, z, ss);
+      }
+      red[0][tid] = s; red[1][tid] = ss;
+      __syncthreads();
+      if (tid < BN && c < cols) {
+#pragma unroll
+        for (int q = 1; q < GROUPS; ++q) { s += red[0][q * BN + c]; ss += red[1][q * BN + c]; }
         p.stat_part[((int64_t)blockIdx.y * 2 + 0) * p.N + n0 + c] = s;
         p.stat_part[((int64_t)blockIdx.y * 2 + 1) * p.N + n0 + c] = ss;
       }
@@ -443,37 +359,50 @@ static cudaError_t launch(const Params& p, dim3 grid, cudaStream_t st) {
 
 }  // namespace tc
 
-__global__ void k_splitk_sum(const float* __restrict__ part, int ksplit, int M, int N,
-                                      const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int accumulate);
+__global__ void k_splitk_sum(const float* __restrict__ part, int ksplit, int M, int N, const float* __restrict__ bias,
+                             float* __restrict__ C, int64_t ldc, int accumulate);
+__global__ void k_splitk_sum_deep(const float* __restrict__ part, int ksplit, int M, int N, const float* __restrict__ bias,
+                                  float* __restrict__ C, int64_t ldc, int accumulate);
 
 static bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // Planning shared by the dry (workspace query) and the real call.
 struct TcPlan { int bn, gm, gn, ksplit; int64_t k_chunk; };
-static TcPlan tc_plan(int M, int N, int64_t K, GemmMode mode) {
+static TcPlan tc_plan(int M, int N, int64_t K, GemmMode mode, bool want_stats) {
   TcPlan pl;
   pl.bn = N > 64 ? 128 : 64;
   pl.gm = (int)cdiv(M, tc::BM);
   pl.gn = (int)cdiv(N, pl.bn);
   const int64_t tiles = (int64_t)pl.gm * pl.gn;
   const int64_t nkb = cdiv(K > 0 ? K : 1, tc::BK);
-  int64_t want = 1;
-  if (tiles < kNumSMs) want = cdiv(2 * kNumSMs, tiles);
-  // the fp32 TMEM accumulator is rounded once per MMA: keep every split's reduction short so the
-  // rounding stays far below the 1e-4 parity bar on the long row reductions of dW = dy^T x.
+  // Split-K by a small cost model (microseconds): waves x (fixed CTA cost + k-blocks x per-block cost) + the
+  // reduction pass.  Small GEMMs on 148 SMs are dominated by wave quantisation, not by flops.
+  const int64_t slots = (int64_t)kNumSMs * (pl.bn == 64 ? 2 : 1);
+  // the fp32 TMEM accumulator is rounded once per MMA: keep every split's reduction short so the rounding
+  // stays far below the 1e-4 parity bar on the long row reductions of dW = dy^T x.
   const int64_t max_chunk_kb = (mode == GEMM_TN) ? 64 : 128;
-  if (cdiv(nkb, want) > max_chunk_kb) want = cdiv(nkb, max_chunk_kb);
-  const int64_t cap = nkb / 2 > 0 ? nkb / 2 : 1;   // at least 2 k-blocks per split
-  if (want > cap) want = cap;
-  if (want > 1024) want = 1024;
-  if (want < 1) want = 1;
-  pl.k_chunk = align_up(cdiv(K > 0 ? K : 1, want), tc::BK);
+  const int64_t s_min = cdiv(nkb, max_chunk_kb);
+  int64_t s_max = nkb / 2 > 0 ? nkb / 2 : 1;       // at least 2 k-blocks per split
+  if (s_max > 1024) s_max = 1024;
+  if (s_max < s_min) s_max = s_min;
+  const double mn_bytes = 4.0 * (double)M * (double)N;
+  double best = 1e30;
+  int64_t best_s = s_min;
+  for (int64_t s = s_min; s <= s_max; s = (s < 16 ? s + 1 : s + s / 8)) {
+    const double waves = (double)cdiv(tiles * s, slots);
+    const double per_cta = 3.0 + 0.8 * (double)cdiv(nkb, s);
+    double cost = waves * per_cta;
+    if (s > 1) cost += 4.0 + (double)(s + 1) * mn_bytes / 3.0e6;   // ~3 TB/s through L2
+    if (s > 1 && want_stats) cost += 12.0;                        // separate column-statistics pass
+    if (cost < best) { best = cost; best_s = s; }
+  }
+  pl.k_chunk = align_up(cdiv(K > 0 ? K : 1, best_s), tc::BK);
   pl.ksplit = (int)cdiv(K > 0 ? K : 1, pl.k_chunk);
   return pl;
 }
 
 static int gemm_tc(const GemmArgs& a, GemmMode mode, Arena& ws, float* stat_part, int* stat_nparts, cudaStream_t st) {
-  const TcPlan pl = tc_plan(a.M, a.N, a.K, mode);
+  const TcPlan pl = tc_plan(a.M, a.N, a.K, mode, stat_nparts != nullptr);
   float* part = nullptr;
   if (pl.ksplit > 1) part = ws.take((int64_t)pl.ksplit * a.M * a.N);
   if (stat_nparts) *stat_nparts = pl.ksplit > 1 ? 0 : pl.gm;
@@ -506,16 +435,20 @@ static int gemm_tc(const GemmArgs& a, GemmMode mode, Arena& ws, float* stat_part
   YOLAT_CHECK_LAUNCH();
   if (pl.ksplit > 1) {
     const int64_t tot = (int64_t)a.M * a.N;
-    k_splitk_sum<<<(unsigned)cdiv(tot, 256), 256, 0, st>>>(part, pl.ksplit, a.M, a.N, a.bias, a.C, a.ldc,
-                                                                    a.accumulate);
+    if (pl.ksplit >= 16) {
+      k_splitk_sum_deep<<<(unsigned)cdiv(tot, 32), dim3(32, 32), 0, st>>>(part, pl.ksplit, a.M, a.N, a.bias, a.C, a.ldc,
+                                                                          a.accumulate);
+    } else {
+      k_splitk_sum<<<(unsigned)cdiv(tot, 256), 256, 0, st>>>(part, pl.ksplit, a.M, a.N, a.bias, a.C, a.ldc, a.accumulate);
+    }
     YOLAT_CHECK_LAUNCH();
   }
   return YOLAT_OK;
 }
 
-// C = sum_z part[z] (+ bias), fixed summation order (deterministic)
+// C = sum_z part[z] (+ bias), fixed summation order (deterministic).  Wide variant: many output elements, few splits.
 __global__ void k_splitk_sum(const float* __restrict__ part, int ksplit, int M, int N,
-                                      const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int accumulate) {
+                             const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int accumulate) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= (int64_t)M * N) return;
   const int m = (int)(idx / N), n = (int)(idx % N);
@@ -533,6 +466,39 @@ __global__ void k_splitk_sum(const float* __restrict__ part, int ksplit, int M, 
   if (bias) s += bias[n];
   float* c = C + (int64_t)m * ldc + n;
   *c = accumulate ? (*c + s) : s;
+}
+
+// Deep variant: few output elements, hundreds of splits (dW of the edge / node layers).  32 x 32 block:
+// tx = output element (coalesced), ty strides over the splits with 4 loads in flight, fp64 combine.
+__global__ void __launch_bounds__(1024) k_splitk_sum_deep(const float* __restrict__ part, int ksplit, int M, int N,
+                                                          const float* __restrict__ bias, float* __restrict__ C,
+                                                          int64_t ldc, int accumulate) {
+  __shared__ double sm[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t idx = blockIdx.x * 32 + (int64_t)tx;
+  const int64_t stride = (int64_t)M * N;
+  double s = 0.0;
+  if (idx < stride) {
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int z = ty;
+    for (; z + 96 < ksplit; z += 128) {
+      const float x0 = part[(int64_t)z * stride + idx], x1 = part[(int64_t)(z + 32) * stride + idx];
+      const float x2 = part[(int64_t)(z + 64) * stride + idx], x3 = part[(int64_t)(z + 96) * stride + idx];
+      s += (double)x0; s1 += (double)x1; s2 += (double)x2; s3 += (double)x3;
+    }
+    for (; z < ksplit; z += 32) s += (double)part[(int64_t)z * stride + idx];
+    s = (s + s1) + (s2 + s3);
+  }
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty != 0 || idx >= stride) return;
+#pragma unroll 4
+  for (int q = 1; q < 32; ++q) s += sm[q][tx];
+  const int m = (int)(idx / N), n = (int)(idx % N);
+  float v = (float)s;
+  if (bias) v += bias[n];
+  float* c = C + (int64_t)m * ldc + n;
+  *c = accumulate ? (*c + v) : v;
 }
 
 static bool gemm_use_tc();

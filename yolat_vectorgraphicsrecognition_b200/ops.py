@@ -61,11 +61,13 @@ class GP2ConvFn(torch.autograd.Function):
             raise L.YolatError('attr_edge_gp2: out_channels must be 32, 64 or 128 (got %d)' % C_)
         tape = torch.empty(max(tape_n, 1), dtype=torch.float32, device=x.device)
         ws = L.workspace.get(ws_n, x.device)
+        # bit 1 = forward only: no per-edge activation is written when autograd will not come back for it
+        mode = int(bool(training)) | (0 if any(ctx.needs_input_grad) else 2)
         L.check(lib.yolat_gp2_fwd(C.byref(P), Cin, Cn, C_, x.data_ptr(), x.stride(0), x_node.data_ptr(),
-                                  x_node.stride(0), L.ptr(attr), L.ptr(ew), graph.ptr(), N, E, int(training),
+                                  x_node.stride(0), L.ptr(attr), L.ptr(ew), graph.ptr(), N, E, mode,
                                   out.data_ptr(), out.stride(0), xn_out.data_ptr(), xn_out.stride(0),
                                   tape.data_ptr(), tape.numel(), ws.data_ptr(), ws.numel(), L.stream()), 'gp2_fwd')
-        ctx.graph, ctx.training, ctx.buffers = graph, int(training), buffers
+        ctx.graph, ctx.training, ctx.buffers = graph, int(bool(training)), buffers
         ctx.dims = (N, E, Cin, Cn, C_)
         ctx.save_for_backward(x, x_node, attr, ew, tape, *params)
         return out, xn_out
