@@ -154,10 +154,30 @@ __global__ void k_bn_apply(const float* __restrict__ z, int64_t ldz, int64_t M, 
   y[r * ldy + c] = v;
 }
 
+__global__ void k_bn_apply4(const float* __restrict__ z, int64_t ldz, int64_t M, int C4, const float* __restrict__ stat,
+                            int relu, float* __restrict__ y, int64_t ldy) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= M * C4) return;
+  const int64_t r = idx / C4;
+  const int c = (int)(idx % C4) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(z + r * ldz + c);
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(stat + c));
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(stat + C4 * 4 + c));
+  float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+  if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+  *reinterpret_cast<float4*>(y + r * ldy + c) = o;
+}
+
 int bn_apply(const float* z, int64_t ldz, int64_t M, int C, const float* stat, int relu, float* y, int64_t ldy,
              cudaStream_t st) {
   if (M * C <= 0) return YOLAT_OK;
-  k_bn_apply<<<(unsigned)cdiv(M * C, 256), 256, 0, st>>>(z, ldz, M, C, stat, relu, y, ldy);
+  const bool vec = (C % 4 == 0) && (ldz % 4 == 0) && (ldy % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(stat)) & 15u) == 0;
+  if (vec) {
+    k_bn_apply4<<<(unsigned)cdiv(M * (C / 4), 256), 256, 0, st>>>(z, ldz, M, C / 4, stat, relu, y, ldy);
+  } else {
+    k_bn_apply<<<(unsigned)cdiv(M * C, 256), 256, 0, st>>>(z, ldz, M, C, stat, relu, y, ldy);
+  }
   YOLAT_CHECK_LAUNCH();
   return YOLAT_OK;
 }

@@ -226,6 +226,9 @@ int edge_bwd_scatter(const GraphView& g, int64_t N, int C, const float* dz1, con
 enum { EF_TAPE = 1, EF_STATS = 2, EF_AGG = 4 };
 bool edge_fused_supported(int C);
 int edge_fused_grid(int64_t E);
+int edge_stats1_grid(int64_t E);
+int edge_stats1(const GraphView& g, int64_t N, int64_t E, const float* pq, const float* attr, const float* w1, int Cin,
+                const float* b1, float* part, cudaStream_t st);
 int edge_fused(const GraphView& g, int64_t N, int64_t E, int flags, const float* pq, const float* attr, const float* w1,
                int Cin, const float* b1, const float* stat1, const float* w2, const float* b2, const float* stat2,
                const float* ew, float* z1, float* z2, float* part, float* out, int64_t ldo, cudaStream_t st);

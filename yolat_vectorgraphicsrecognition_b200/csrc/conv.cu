@@ -81,12 +81,13 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
     if (edge_fused_supported(C) && gemm_fused_enabled()) {
       // K-EDGE fused path (edge_fused.cu): pass A = BN1 statistics (no [E,C] store), then the tcgen05 kernel
       // once for the BN2 statistics and once for the segmented mean; z1 / z2 reach HBM only as backward tape.
-      const int ngrid = edge_fused_grid(E);
+      const int ngrid = edge_fused_grid(E), ngrid1 = edge_stats1_grid(E);
       float* part2 = ws.take((int64_t)ngrid * 2 * C);
+      float* part1f = ws.take((int64_t)ngrid1 * 2 * C);
       if (!dry) {
         if (ws.overflow) return YOLAT_ERR_WORKSPACE;
-        if (training) YOLAT_TRY(edge_z1(g, N, C, pq, attr, p->w1, Cin, p->b1, nullptr, part1, st));
-        YOLAT_TRY(bn_finalize_from_partials(part1, nparts, E, C, &p->bn1, training, t.stat1, st));
+        if (training) YOLAT_TRY(edge_stats1(g, N, E, pq, attr, p->w1, Cin, p->b1, part1f, st));
+        YOLAT_TRY(bn_finalize_from_partials(part1f, ngrid1, E, C, &p->bn1, training, t.stat1, st));
         if (training) {
           YOLAT_TRY(edge_fused(g, N, E, EF_STATS | (no_tape ? 0 : EF_TAPE), pq, attr, p->w1, Cin, p->b1, t.stat1, p->w2,
                                p->b2, nullptr, ew, t.z1, t.z2, part2, nullptr, 0, st));

@@ -325,6 +325,73 @@ __global__ void __launch_bounds__(THREADS, 2) k_edge_fused(const Params p) {
   if (warp == 0) tmem_dealloc(tmem_d, C);
 }
 
+// ---- pass A: BatchNorm-1 batch statistics of z1 (gather only, nothing stored) ------------------------------
+// thread = (16-byte channel chunk gc, slot lane); 4 slots per thread in flight; per-thread channel sums are
+// combined per CTA and written as one partial [2][C] (fp64 combine in k_bn_finalize).
+constexpr int S1_THREADS = 256;
+__global__ void __launch_bounds__(S1_THREADS, 3) k_edge_stats1(const Params p) {
+  __shared__ float red[2][S1_THREADS / 16][C];
+  const int tid = threadIdx.x, gc = tid & 15, sl = tid >> 4;
+  float w1c[4][4], bias1[4], s[4], ss[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int ch = gc * 4 + q;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w1c[q][k] = __ldg(p.w1c + ch * p.ld1 + k);
+    bias1[q] = p.b1 ? __ldg(p.b1 + ch) : 0.f;
+    s[q] = 0.f; ss[q] = 0.f;
+  }
+  const int64_t s_begin = p.E * (int64_t)blockIdx.x / gridDim.x;
+  const int64_t s_end = p.E * (int64_t)(blockIdx.x + 1) / gridDim.x;
+  for (int64_t s0 = s_begin; s0 < s_end; s0 += 64) {
+    int dsts[4], srcs[4], eids[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t slot = s0 + sl + 16 * i;
+      const bool ok = slot < s_end;
+      dsts[i] = ok ? __ldg(p.dst + slot) : -1;
+      srcs[i] = ok ? __ldg(p.src + slot) : 0;
+      eids[i] = ok ? __ldg(p.eid + slot) : 0;
+    }
+    float4 pv[4], qv[4], av[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pv[i] = qv[i] = av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dsts[i] >= 0) {
+        pv[i] = __ldg(reinterpret_cast<const float4*>(p.pq + (int64_t)dsts[i] * (2 * C) + gc * 4));
+        qv[i] = __ldg(reinterpret_cast<const float4*>(p.pq + (int64_t)srcs[i] * (2 * C) + C + gc * 4));
+        av[i] = __ldg(reinterpret_cast<const float4*>(p.attr + (int64_t)eids[i] * 4));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (dsts[i] < 0) continue;
+      const float pp[4] = {pv[i].x, pv[i].y, pv[i].z, pv[i].w};
+      const float qq[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v = (pp[q] + bias1[q]) + qq[q];
+        v = fmaf(av[i].x, w1c[q][0], v);
+        v = fmaf(av[i].y, w1c[q][1], v);
+        v = fmaf(av[i].z, w1c[q][2], v);
+        v = fmaf(av[i].w, w1c[q][3], v);
+        s[q] += v;
+        ss[q] = fmaf(v, v, ss[q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { red[0][sl][gc * 4 + q] = s[q]; red[1][sl][gc * 4 + q] = ss[q]; }
+  __syncthreads();
+  if (tid < 2 * C) {
+    const int which = tid / C, c = tid % C;
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < S1_THREADS / 16; ++k) a += red[which][k][c];
+    p.part[((int64_t)blockIdx.x * 2 + which) * C + c] = a;
+  }
+}
+
 template <int FLAGS>
 static cudaError_t launch(const Params& p, int grid, cudaStream_t st) {
   static bool configured = false;
@@ -345,6 +412,25 @@ int edge_fused_grid(int64_t E) {
   const int64_t tiles = cdiv(E > 0 ? E : 1, ef::TILE);
   const int64_t cap = 2 * (int64_t)kNumSMs;       // two resident CTAs per SM (98 KB of shared memory each)
   return (int)(tiles < cap ? tiles : cap);
+}
+
+int edge_stats1_grid(int64_t E) {
+  const int64_t need = cdiv(E > 0 ? E : 1, 64);
+  const int64_t cap = 3 * (int64_t)kNumSMs;
+  return (int)(need < cap ? need : cap);
+}
+
+// part: [edge_stats1_grid(E)][2][C] sums / sums of squares of z1 over all edges
+int edge_stats1(const GraphView& g, int64_t N, int64_t E, const float* pq, const float* attr, const float* w1, int Cin,
+                const float* b1, float* part, cudaStream_t st) {
+  if (E <= 0) return YOLAT_OK;
+  ef::Params p{};
+  p.rowptr = g.rowptr_t; p.src = g.src_t; p.dst = g.dst_t; p.eid = g.eid_t; p.deg_inv = g.deg_inv;
+  p.N = N; p.E = E; p.pq = pq; p.attr = attr;
+  p.w1c = w1 + 2 * Cin; p.ld1 = 2 * Cin + 4; p.b1 = b1; p.part = part;
+  ef::k_edge_stats1<<<edge_stats1_grid(E), ef::S1_THREADS, 0, st>>>(p);
+  YOLAT_CHECK_LAUNCH();
+  return YOLAT_OK;
 }
 
 // flags: EF_TAPE | EF_STATS | EF_AGG (common.cuh).  part: [edge_fused_grid(E)][2][C] when EF_STATS.

@@ -370,7 +370,8 @@ static bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) &
 struct TcPlan { int bn, gm, gn, ksplit; int64_t k_chunk; };
 static TcPlan tc_plan(int M, int N, int64_t K, GemmMode mode, bool want_stats) {
   TcPlan pl;
-  pl.bn = N > 64 ? 128 : 64;
+  static const int force_bn = getenv("YOLAT_TC_BN") ? atoi(getenv("YOLAT_TC_BN")) : 0;   // tuning knob
+  pl.bn = force_bn == 64 ? 64 : (N > 64 ? 128 : 64);
   pl.gm = (int)cdiv(M, tc::BM);
   pl.gn = (int)cdiv(N, pl.bn);
   const int64_t tiles = (int64_t)pl.gm * pl.gn;

@@ -62,7 +62,8 @@ class AttrRelativeEdgeConvGlobalPool2(nn.Module):
             x = x[1]
         graph = graph_for(edge_index, x.shape[0])
         params, buffers = self._flat()
-        return ops.GP2ConvFn.apply(graph, self.training, buffers, x, x_node, edge_attr, edge_weight, *params)
+        return ops.GP2ConvFn.apply(graph, self.training, torch.is_grad_enabled(), buffers, x, x_node, edge_attr,
+                                   edge_weight, *params)
 
     def __repr__(self):
         return '{}(nn={})'.format(self.__class__.__name__, self.nn)

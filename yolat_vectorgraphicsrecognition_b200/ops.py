@@ -26,12 +26,14 @@ def _empty_like_param(p):
 # GraphConv('attr_edge_gp2')   gcn_lib/sparse/torch_vertex.py:288-341
 # --------------------------------------------------------------------------------------------------
 class GP2ConvFn(torch.autograd.Function):
-    """(x, x_node, attr, edge_weight, 14 parameters) -> (out, x_node_out); buffers are updated in place."""
+    """(x, x_node, attr, edge_weight, 14 parameters) -> (out, x_node_out); buffers are updated in place.
+    `save_tape` = autograd is recording (torch.is_grad_enabled() at the call site): without it the forward runs the
+    fully fused K-EDGE passes and writes no per-edge activation."""
 
     N_PARAMS = 14
 
     @staticmethod
-    def forward(ctx, graph, training, buffers, x, x_node, attr, edge_weight, *params):
+    def forward(ctx, graph, training, save_tape, buffers, x, x_node, attr, edge_weight, *params):
         (w1, b1, g1, be1, w2, b2, g2, be2, wr, br, wn, bnode, gn, ben) = params
         (rm1, rv1, nbt1, rm2, rv2, nbt2, rmn, rvn, nbtn) = buffers
         L.require_cuda(x, x_node, attr, w1)
@@ -62,7 +64,7 @@ class GP2ConvFn(torch.autograd.Function):
         tape = torch.empty(max(tape_n, 1), dtype=torch.float32, device=x.device)
         ws = L.workspace.get(ws_n, x.device)
         # bit 1 = forward only: no per-edge activation is written when autograd will not come back for it
-        mode = int(bool(training)) | (0 if any(ctx.needs_input_grad) else 2)
+        mode = int(bool(training)) | (0 if (save_tape and any(ctx.needs_input_grad)) else 2)
         L.check(lib.yolat_gp2_fwd(C.byref(P), Cin, Cn, C_, x.data_ptr(), x.stride(0), x_node.data_ptr(),
                                   x_node.stride(0), L.ptr(attr), L.ptr(ew), graph.ptr(), N, E, mode,
                                   out.data_ptr(), out.stride(0), xn_out.data_ptr(), xn_out.stride(0),
@@ -87,7 +89,7 @@ class GP2ConvFn(torch.autograd.Function):
                         L.ptr(wn), L.ptr(bnode), _bn_struct(gn, ben, rmn, rvn, None))
         grads = [_empty_like_param(p) for p in params]
         G = L.Gp2Grads(*[g.data_ptr() for g in grads])
-        need_dx, need_dxn = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        need_dx, need_dxn = ctx.needs_input_grad[4], ctx.needs_input_grad[5]
         dx = torch.empty_like(x) if need_dx else None
         dxn = torch.empty_like(x_node) if need_dxn else None
         ws = L.workspace.get(lib.yolat_gp2_bwd_ws_floats(N, E, Cin, Cn, C_), x.device)
@@ -96,7 +98,7 @@ class GP2ConvFn(torch.autograd.Function):
                                   g_out.data_ptr(), g_out.stride(0), g_xn.data_ptr(), g_xn.stride(0),
                                   L.ptr(dx), Cin, L.ptr(dxn), Cn, 0, tape.data_ptr(), ws.data_ptr(), ws.numel(),
                                   L.stream()), 'gp2_bwd')
-        return (None, None, None, dx, dxn, None, None) + tuple(grads)
+        return (None, None, None, None, dx, dxn, None, None) + tuple(grads)
 
 
 # --------------------------------------------------------------------------------------------------
