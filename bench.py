@@ -34,6 +34,8 @@ def parse():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--graphs', type=int, default=4, help='graphs per rank per step')
+    ap.add_argument('--mode', default='graph', choices=['graph', 'eager'],
+                    help='graph: the step is replayed as one CUDA graph (GraphedStep); eager: launched from Python')
     ap.add_argument('--cpu-steps', type=int, default=8, help='timed steps of the cpu_baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -144,6 +146,21 @@ class Clocks(object):
 # ---------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------
+def edge_path_bytes(N, E, Cin, C):
+    """Algorithmic bytes of the edge path alone: x + edge_index (int64 as delivered) + e_attr + out."""
+    return 4 * N * Cin + 16 * E + 16 * E + 4 * N * C
+
+
+def ncu_traffic():
+    """dram bytes (read + write) per launch of the roofline kernel from the committed `ncu --set full` capture
+    (profiles/edge_fused_traffic.json, written by profiles/extract_traffic.py); None when no capture exists."""
+    p = os.path.join(ROOT, 'profiles', 'edge_fused_traffic.json')
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get('dram_bytes_per_launch')
+
+
 def edge_bytes(N, E, Cin, Cn, C):
     """Algorithmic bytes of one GraphConv('attr_edge_gp2') forward: x + edge_index (int64 as
     delivered) + e_attr + out, plus the node branch x_node + x_node_out."""
@@ -156,7 +173,8 @@ def main():
         return run_reference_arm(args)
 
     import torch.distributed as dist
-    from yolat_vectorgraphicsrecognition_b200 import _lib, synth, ops
+    from yolat_vectorgraphicsrecognition_b200 import _lib, synth, dp
+    from yolat_vectorgraphicsrecognition_b200.graphed import GraphedStep
     from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
     from yolat_vectorgraphicsrecognition_b200.graph import CSRGraph
     if not torch.cuda.is_available():
@@ -178,27 +196,54 @@ def main():
     host = synth.floorplans_batch(graphs=args.graphs, seed=1 if world == 1 else 1000 + rank).pin_memory()
     resident = host.to(dev)
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    flat = dp.FlatGradients(params) if world > 1 else None
 
-    def step(batch):
+    def eager_step(batch):
         for p in params:
             p.grad = None
         out = model(batch, None)
         loss = crit(out, batch)['loss']
         loss.backward()
-        if world > 1:
-            flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
-            dist.all_reduce(flat)
-            flat.mul_(1.0 / world)
-            for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, params)):
-                p.grad = g
+        if flat is not None:
+            flat.all_reduce_mean()
         return loss
+
+    # The step is ~150 short kernels: eager launching is host-bound, so the product path replays it as one CUDA
+    # graph (graphed.py); the gradient all-reduce of N > 1 follows the replay on the same stream.
+    graphed = GraphedStep(model, crit)
+
+    def graph_step(batch):
+        loss = graphed(batch)
+        if flat is not None:
+            flat.all_reduce_mean()
+        return loss
+
+    step = eager_step if args.mode == 'eager' else graph_step
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, batch, steps):
+        """K steps, each bracketed by CUDA events on the launching stream, L2 flushed (untimed) in between."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            fn(batch)
+            b.record()
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- device-resident timing: value ------------------------------------------------------------
+    l0 = lib.yolat_launch_count()
+    eager_step(resident)
+    launches = lib.yolat_launch_count() - l0           # kernels of this library per step (the graph replays the same)
     for _ in range(max(args.warmup, 3)):
         step(resident)
     barrier()
@@ -206,36 +251,26 @@ def main():
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    launches0 = lib.yolat_launch_count()
     t_wall0 = time.perf_counter()
-    for a, b in ev:
-        flush.zero_()                    # evict L2 between timed steps (untimed)
-        a.record()
-        step(resident)
-        b.record()
-    barrier()
+    ms = timed(step, resident, args.steps)
     t_wall1 = time.perf_counter()
-    launches = (lib.yolat_launch_count() - launches0) // max(args.steps, 1)
-    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+    other = eager_step if step is graph_step else graph_step
+    for _ in range(3):
+        other(resident)
+    ms_other = timed(other, resident, max(3, args.steps // 2))
 
     # ---- end to end through the public API with host buffers: e2e -----------------------------------
     e2e = None
     if not args.no_e2e:
         for _ in range(3):
-            float(step(host))
+            float(step(host).detach())
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(args.steps):
-            loss = step(host)            # .cuda() copies of the pinned host tensors happen inside forward / loss
-            float(loss)                  # D2H read of the step's result (train.py:286)
+            loss = step(host)            # H2D copies of the pinned host tensors happen inside the step
+            float(loss.detach())         # D2H read of the step's result (train.py:286)
         b.record()
         barrier()
         t = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device=dev)
@@ -246,7 +281,7 @@ def main():
         e2e = {'value': args.graphs * world / (float(t.item()) * 1e-3), 'unit': 'graphs/s',
                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'ms_per_step': float(t.item())}
 
-    # ---- roofline of the scatter path: one block-layer GraphConv forward (edge + node branch) -----------
+    # ---- roofline of the scatter path: the K-EDGE kernels of one block-layer GraphConv forward ----------
     roof = None
     if rank == 0:
         hbm, which = peaks()
@@ -257,9 +292,12 @@ def main():
         xin = torch.randn(Nn, 64, device=dev)
         xnode = torch.randn(Nn, 64, device=dev)
         graph = CSRGraph(big.edge.T, Nn)
+        import ctypes as C
         with torch.no_grad():
             for _ in range(3):
                 conv(xin, graph, None, big.e_attr, x_node=xnode)
+            torch.cuda.synchronize()
+            lib.yolat_prof_enable(1)     # CUDA events around the K-EDGE launches, on the launching stream
             reps, tot = 10, 0.0
             for _ in range(reps):
                 flush.zero_()
@@ -269,13 +307,28 @@ def main():
                 b.record()
                 torch.cuda.synchronize()
                 tot += a.elapsed_time(b)
-        k_ms = tot / reps
-        nbytes = edge_bytes(Nn, Ee, 64, 64, 64)
+            lib.yolat_prof_enable(0)
+        per_kernel = {}
+        for name, kid in (('k_edge_stats1', 0), ('k_edge_fused<F_STATS>', 1), ('k_edge_fused<F_AGG>', 2)):
+            n, t = C.c_int64(0), C.c_double(0.0)
+            lib.yolat_prof_read(kid, C.byref(n), C.byref(t))
+            per_kernel[name] = {'launches': int(n.value), 'ms': (t.value / n.value) if n.value else None}
+        op_ms = tot / reps
+        k_ms = per_kernel['k_edge_fused<F_AGG>']['ms']
+        nbytes = edge_path_bytes(Nn, Ee, 64, 64)
         ach = nbytes / (k_ms * 1e-3) / 1e9
-        roof = {'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None,
-                'kernel': 'yolat_gp2_fwd (block layer 64->64, training): gather + edge MLP + BN + mean-scatter + node branch',
+        op_bytes = edge_bytes(Nn, Ee, 64, 64, 64)
+        roof = {'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm,
+                'traffic': ncu_traffic(),
+                'kernel': 'ef::k_edge_fused<F_AGG> (K-EDGE pass C: gather + Lin1 + BN1/ReLU + tcgen05 Lin2 + BN2/ReLU + '
+                          'segmented mean-scatter) of one block-layer GraphConv(64->64) forward, training mode',
                 'algorithmic_bytes': nbytes, 'ms': k_ms, 'peak_source': which,
-                'shape': {'N': Nn, 'E': Ee, 'graphs': sg}, 'l2': 'flushed before every launch'}
+                'shape': {'N': Nn, 'E': Ee, 'graphs': sg}, 'l2': 'flushed before every call',
+                'timing': 'CUDA events recorded around the launch on its own stream (yolat_prof_*), avg of %d' % reps,
+                'passes': per_kernel,
+                'whole_op': {'what': 'yolat_gp2_fwd: lin_r + P/Q GEMMs, passes A/B/C, BN finalizes, node branch',
+                             'ms': op_ms, 'algorithmic_bytes': op_bytes,
+                             'achieved': op_bytes / (op_ms * 1e-3) / 1e9, 'frac': op_bytes / (op_ms * 1e-3) / 1e9 / hbm}}
         del big, xin, xnode, graph
 
     # ---- CPU baseline (rank 0, N = 1) -------------------------------------------------------------------
@@ -291,8 +344,11 @@ def main():
             'config': {'workload': WORKLOAD, 'step': 'fwd+loss+bwd' + ('+nccl grad all-reduce' if world > 1 else ''),
                        'graphs_per_step_per_gpu': args.graphs, 'in_channels': 5, 'n_blocks': 2, 'n_filters': 64,
                        'n_classes': 17, 'l2': 'flushed between timed steps (256 MiB memset, untimed)',
+                       'launch': 'one CUDA-graph replay per step' if args.mode == 'graph' else 'eager',
                        'parallelism': 'dp%d' % world},
             'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
+            'launch_mode': args.mode,
+            'other_mode': {'mode': 'eager' if args.mode == 'graph' else 'graph', 'ms_per_step': ms_other},
         }
         print(json.dumps(line))
     if world > 1:

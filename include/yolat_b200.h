@@ -38,6 +38,17 @@ const char* yolat_last_cuda_error(void);
 /* number of kernels this library has launched in this process (bench.py reports the per-step delta) */
 int64_t yolat_launch_count(void);
 
+/* Opt-in per-kernel device timing (CUDA events recorded on the launching stream around the kernels named
+ * below; bench.py uses it for the roofline of the dominant kernel, which is launched from inside
+ * yolat_gp2_fwd).  yolat_prof_enable(1) starts a fresh window, yolat_prof_read synchronises the recorded
+ * events and returns the number of launches and their summed duration.  Never enable during graph capture. */
+#define YOLAT_PROF_EDGE_STATS1 0       /* ef::k_edge_stats1          (K-EDGE pass A)            */
+#define YOLAT_PROF_EDGE_FUSED_STATS 1  /* ef::k_edge_fused<F_STATS>  (K-EDGE pass B)            */
+#define YOLAT_PROF_EDGE_FUSED_AGG 2    /* ef::k_edge_fused<F_AGG>    (K-EDGE pass C, the scatter) */
+#define YOLAT_PROF_GEMM 3              /* tc::k_tc_gemm (any mode)                              */
+int yolat_prof_enable(int on);
+int yolat_prof_read(int id, int64_t* launches, double* total_ms);
+
 /* ------------------------------------------------------------------------------------------------
  * Graph preparation.  Replaces what PyG's MessagePassing.propagate does implicitly on every call
  * (gather by edge_index[0]/[1], scatter by edge_index[1]; gcn_lib/sparse/torch_vertex.py:324) with a

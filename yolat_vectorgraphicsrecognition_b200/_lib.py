@@ -37,6 +37,8 @@ _SIGS = {
     'yolat_status_string': (C.c_char_p, [C.c_int]),
     'yolat_last_cuda_error': (C.c_char_p, []),
     'yolat_launch_count': (i64, []),
+    'yolat_prof_enable': (C.c_int, [C.c_int]),
+    'yolat_prof_read': (C.c_int, [C.c_int, C.POINTER(i64), C.POINTER(C.c_double)]),
     'yolat_graph_ints': (i64, [i64, i64]),
     'yolat_graph_build': (C.c_int, [vp, i64, i64, i64, i64, vp, vp]),
     'yolat_graph_error_ptr': (vp, [vp, i64, i64]),

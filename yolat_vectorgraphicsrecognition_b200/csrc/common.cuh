@@ -17,6 +17,13 @@ constexpr int kNumSMs = 148;          // B200
 void set_last_error(cudaError_t e);
 void count_launch();   // process-wide kernel-launch counter behind yolat_launch_count()
 
+// Opt-in device timing of one launch (prof.cu); ids are the YOLAT_PROF_* constants of the public header.
+struct ProfScope {
+  ProfScope(int id, cudaStream_t st);
+  ~ProfScope();
+  cudaStream_t st_; bool active_; size_t idx_;
+};
+
 #define YOLAT_CHECK_LAUNCH()                                  \
   do {                                                        \
     cudaError_t _e = cudaGetLastError();                      \

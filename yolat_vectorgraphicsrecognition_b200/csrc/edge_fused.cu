@@ -428,6 +428,7 @@ int edge_stats1(const GraphView& g, int64_t N, int64_t E, const float* pq, const
   p.rowptr = g.rowptr_t; p.src = g.src_t; p.dst = g.dst_t; p.eid = g.eid_t; p.deg_inv = g.deg_inv;
   p.N = N; p.E = E; p.pq = pq; p.attr = attr;
   p.w1c = w1 + 2 * Cin; p.ld1 = 2 * Cin + 4; p.b1 = b1; p.part = part;
+  ProfScope prof(YOLAT_PROF_EDGE_STATS1, st);
   ef::k_edge_stats1<<<edge_stats1_grid(E), ef::S1_THREADS, 0, st>>>(p);
   YOLAT_CHECK_LAUNCH();
   return YOLAT_OK;
@@ -446,6 +447,7 @@ int edge_fused(const GraphView& g, int64_t N, int64_t E, int flags, const float*
   p.z1 = z1; p.z2 = z2; p.part = part; p.out = out; p.ldo = ldo;
   const int grid = edge_fused_grid(E);
   cudaError_t e;
+  ProfScope prof((flags & EF_AGG) ? YOLAT_PROF_EDGE_FUSED_AGG : YOLAT_PROF_EDGE_FUSED_STATS, st);
   switch (flags) {
     case EF_STATS: e = ef::launch<ef::F_STATS>(p, grid, st); break;
     case EF_STATS | EF_TAPE: e = ef::launch<ef::F_STATS | ef::F_TAPE>(p, grid, st); break;

@@ -422,6 +422,7 @@ static int gemm_tc(const GemmArgs& a, GemmMode mode, Arena& ws, float* stat_part
   p.c_vec = aligned16p(a.C) && (a.ldc % 4 == 0);
   dim3 grid(pl.gn, pl.gm, pl.ksplit);
   cudaError_t e = cudaSuccess;
+  ProfScope prof(YOLAT_PROF_GEMM, st);
 #define YOLAT_TC_CASE(MODE_)                                                    \
   case MODE_:                                                                   \
     e = pl.bn == 128 ? tc::launch<MODE_, 128>(p, grid, st) : tc::launch<MODE_, 64>(p, grid, st); \
