@@ -59,11 +59,24 @@ def main():
     print('N=%d E=%d algorithmic fwd bytes=%.1f MB' % (N, E, nbytes / 1e6))
 
     if 'fwd_notape' in what:
+        import ctypes as C
+        from yolat_vectorgraphicsrecognition_b200 import _lib
+        lib = _lib.lib()
+
         def f(_):
             with torch.no_grad():
                 conv(xin, graph, None, big.e_attr, x_node=xnode)
+        f(None)
+        torch.cuda.synchronize()
+        lib.yolat_prof_enable(1)
         ms = timed(f)
+        lib.yolat_prof_enable(0)
         print('fwd train no-tape : %.3f ms  %.0f GB/s algorithmic' % (ms, nbytes / ms / 1e6))
+        for name, kid in (('k_edge_stats1', 0), ('k_edge_fused<STATS>', 1), ('k_edge_fused<AGG>', 2), ('k_tc_gemm', 3)):
+            n, t = C.c_int64(0), C.c_double(0.0)
+            lib.yolat_prof_read(kid, C.byref(n), C.byref(t))
+            if n.value:
+                print('    %-22s %3d launches, avg %.1f us' % (name, n.value, 1e3 * t.value / n.value))
     if 'fwd_tape' in what:
         xr = xin.clone().requires_grad_(True)
         xnr = xnode.clone().requires_grad_(True)

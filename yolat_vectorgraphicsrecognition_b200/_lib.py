@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libyolat_b200.so')
+LIB_PATH = os.environ.get('YOLAT_B200_LIB') or os.path.join(_HERE, 'libyolat_b200.so')   # override: kernel experiments
 
 i64, i32, f32p, vp = C.c_int64, C.c_int, C.c_void_p, C.c_void_p
 

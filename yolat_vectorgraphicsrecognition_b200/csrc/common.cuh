@@ -219,26 +219,31 @@ int relu_fwd(float* y, int64_t ldy, int64_t M, int C, cudaStream_t st);
 int relu_bwd(const float* gy, int64_t ldgy, const float* z, int64_t ldz, int64_t M, int C, float* dz, int64_t lddz,
              cudaStream_t st);
 // edge.cu launchers
-int edge_prep_wpq(const float* w1, int Cin, int C, float* wpq, cudaStream_t st);
+// wr / br / bias3 optional (null): append the lin_r rows so that one GEMM yields P | Q | lin_r(x)
+int edge_prep_wpq(const float* w1, int Cin, int C, float* wpq, const float* wr, const float* br, float* bias3,
+                  cudaStream_t st);
 int edge_assemble_dw1(const float* dwpq, const float* dw1c, int Cin, int C, float* dw1, cudaStream_t st);
 int edge_z1_nparts(int64_t N);
 int edge_z1(const GraphView& g, int64_t N, int C, const float* pq, const float* attr, const float* w1, int Cin,
             const float* b1, float* z1, float* part, cudaStream_t st);
-int edge_agg(const GraphView& g, int64_t N, int C, const float* z2, const float* stat2, const float* ew, float* out,
-             int64_t ldo, cudaStream_t st);
+int edge_agg(const GraphView& g, int64_t N, int C, const float* z2, const float* stat2, const float* ew,
+             const float* base, int64_t ldb, float* out, int64_t ldo, cudaStream_t st);
 int edge_bwd_scatter(const GraphView& g, int64_t N, int C, const float* dz1, const float* attr, float* dpq,
                      float* part, float* dw1c, cudaStream_t st);
 
 // edge_fused.cu: the fused gather -> edge MLP (tcgen05) -> statistics / segmented mean kernel (C == 64)
 enum { EF_TAPE = 1, EF_STATS = 2, EF_AGG = 4 };
 bool edge_fused_supported(int C);
+bool edge_fused_fits(int64_t N, int64_t ldpq);
 int edge_fused_grid(int64_t E);
 int edge_stats1_grid(int64_t E);
-int edge_stats1(const GraphView& g, int64_t N, int64_t E, const float* pq, const float* attr, const float* w1, int Cin,
-                const float* b1, float* part, cudaStream_t st);
-int edge_fused(const GraphView& g, int64_t N, int64_t E, int flags, const float* pq, const float* attr, const float* w1,
-               int Cin, const float* b1, const float* stat1, const float* w2, const float* b2, const float* stat2,
-               const float* ew, float* z1, float* z2, float* part, float* out, int64_t ldo, cudaStream_t st);
+int edge_stats1(const GraphView& g, int64_t N, int64_t E, const float* pq, int64_t ldpq, const float* attr,
+                const float* w1, int Cin, const float* b1, float* part, cudaStream_t st);
+// EF_AGG: out = base + mean (base may alias out or be null); every row of out is written exactly once
+int edge_fused(const GraphView& g, int64_t N, int64_t E, int flags, const float* pq, int64_t ldpq, const float* attr,
+               const float* w1, int Cin, const float* b1, const float* stat1, const float* w2, const float* b2,
+               const float* stat2, const float* ew, float* z1, float* z2, float* part, const float* base, int64_t ldb,
+               float* out, int64_t ldo, cudaStream_t st);
 
 int colsum(const float* a, int64_t lda, int64_t M, int C, float* out, Arena& ws, cudaStream_t st);
 int fill_zero(float* p, int64_t n, cudaStream_t st);

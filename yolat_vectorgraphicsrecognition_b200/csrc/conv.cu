@@ -53,8 +53,17 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
   const bool no_tape = (mode & YOLAT_GP2_NO_TAPE) != 0;   // forward only: z1 / z2 are never written
   Gp2Tape t;
   gp2_tape_layout(tape, N, E, C, &t);
-  float* wpq = ws.take((int64_t)2 * C * Cin);
-  float* pq = ws.take(N * 2 * C);
+  // Fused path: one GEMM x [Wp; Wq; Wr]^T -> P | Q | lin_r(x) (row stride 3C); the aggregation adds the lin_r column
+  // block while writing `out`.  Unfused path (C = 32 / 128): lin_r goes straight to `out`, P | Q has row stride 2C.
+  // (Folding lin_r into the P | Q GEMM -- kFusePqr -- was measured slower at the > L2 scale: the third 64-column block
+  // wastes half of a 128-wide MMA tile and the wider rows cost the Q gathers their L2 residency.)
+  constexpr bool kFusePqr = false;
+  const bool fused = E > 0 && edge_fused_supported(C) && edge_fused_fits(N, 3 * C) && gemm_fused_enabled();
+  const bool pqr = fused && kFusePqr;
+  const int ldpq = pqr ? 3 * C : 2 * C;
+  float* wpq = ws.take((int64_t)3 * C * Cin);
+  float* bias3 = ws.take(3 * C);
+  float* pq = ws.take(N * ldpq);
   const int nparts = edge_z1_nparts(N);
   float* part1 = ws.take((int64_t)nparts * 2 * C);
   if (!dry && (ws.overflow || tape.overflow)) return YOLAT_ERR_WORKSPACE;
@@ -63,7 +72,7 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
   if (!dry) graph_layout(N, E, graph, &g);
 
   // ---- lin_r: out = x Wr^T + br  (torch_vertex.py:325) ------------------------------------------
-  {
+  if (!pqr) {
     GemmArgs a{};
     a.A = x; a.lda = ldx; a.B = dry ? nullptr : p->wr; a.ldb = Cin; a.C = out; a.ldc = ldo;
     a.M = (int)N; a.N = C; a.K = Cin; a.bias = dry ? nullptr : p->br;
@@ -71,37 +80,39 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
   }
   // ---- edge path ---------------------------------------------------------------------------------
   if (E > 0) {
-    if (!dry) YOLAT_TRY(edge_prep_wpq(p->w1, Cin, C, wpq, st));
+    if (!dry) YOLAT_TRY(edge_prep_wpq(p->w1, Cin, C, wpq, pqr ? p->wr : nullptr, p->br, bias3, st));
     {
       GemmArgs a{};
-      a.A = x; a.lda = ldx; a.B = wpq; a.ldb = Cin; a.C = pq; a.ldc = 2 * C;
-      a.M = (int)N; a.N = 2 * C; a.K = Cin;
+      a.A = x; a.lda = ldx; a.B = wpq; a.ldb = Cin; a.C = pq; a.ldc = ldpq;
+      a.M = (int)N; a.N = ldpq; a.K = Cin; a.bias = pqr ? bias3 : nullptr;
       YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
     }
-    if (edge_fused_supported(C) && gemm_fused_enabled()) {
+    if (fused) {
       // K-EDGE fused path (edge_fused.cu): pass A = BN1 statistics (no [E,C] store), then the tcgen05 kernel
       // once for the BN2 statistics and once for the segmented mean; z1 / z2 reach HBM only as backward tape.
       const int ngrid = edge_fused_grid(E), ngrid1 = edge_stats1_grid(E);
       float* part2 = ws.take((int64_t)ngrid * 2 * C);
       float* part1f = ws.take((int64_t)ngrid1 * 2 * C);
+      const float* base = pqr ? pq + 2 * C : out;       // lin_r(x): third column block, or already in `out`
+      const int64_t ldbase = pqr ? ldpq : ldo;
       if (!dry) {
         if (ws.overflow) return YOLAT_ERR_WORKSPACE;
-        if (training) YOLAT_TRY(edge_stats1(g, N, E, pq, attr, p->w1, Cin, p->b1, part1f, st));
+        if (training) YOLAT_TRY(edge_stats1(g, N, E, pq, ldpq, attr, p->w1, Cin, p->b1, part1f, st));
         YOLAT_TRY(bn_finalize_from_partials(part1f, ngrid1, E, C, &p->bn1, training, t.stat1, st));
         if (training) {
-          YOLAT_TRY(edge_fused(g, N, E, EF_STATS | (no_tape ? 0 : EF_TAPE), pq, attr, p->w1, Cin, p->b1, t.stat1, p->w2,
-                               p->b2, nullptr, ew, t.z1, t.z2, part2, nullptr, 0, st));
+          YOLAT_TRY(edge_fused(g, N, E, EF_STATS | (no_tape ? 0 : EF_TAPE), pq, ldpq, attr, p->w1, Cin, p->b1, t.stat1,
+                               p->w2, p->b2, nullptr, ew, t.z1, t.z2, part2, nullptr, 0, nullptr, 0, st));
           YOLAT_TRY(bn_finalize_from_partials(part2, ngrid, E, C, &p->bn2, 1, t.stat2, st));
           if (no_tape) {
-            YOLAT_TRY(edge_fused(g, N, E, EF_AGG, pq, attr, p->w1, Cin, p->b1, t.stat1, p->w2, p->b2, t.stat2, ew,
-                                 nullptr, nullptr, nullptr, out, ldo, st));
+            YOLAT_TRY(edge_fused(g, N, E, EF_AGG, pq, ldpq, attr, p->w1, Cin, p->b1, t.stat1, p->w2, p->b2, t.stat2, ew,
+                                 nullptr, nullptr, nullptr, base, ldbase, out, ldo, st));
           } else {
-            YOLAT_TRY(edge_agg(g, N, C, t.z2, t.stat2, ew, out, ldo, st));
+            YOLAT_TRY(edge_agg(g, N, C, t.z2, t.stat2, ew, base, ldbase, out, ldo, st));
           }
         } else {
           YOLAT_TRY(bn_finalize_from_partials(nullptr, 0, E, C, &p->bn2, 0, t.stat2, st));
-          YOLAT_TRY(edge_fused(g, N, E, EF_AGG | (no_tape ? 0 : EF_TAPE), pq, attr, p->w1, Cin, p->b1, t.stat1, p->w2,
-                               p->b2, t.stat2, ew, t.z1, t.z2, nullptr, out, ldo, st));
+          YOLAT_TRY(edge_fused(g, N, E, EF_AGG | (no_tape ? 0 : EF_TAPE), pq, ldpq, attr, p->w1, Cin, p->b1, t.stat1,
+                               p->w2, p->b2, t.stat2, ew, t.z1, t.z2, nullptr, base, ldbase, out, ldo, st));
         }
       }
     } else {
@@ -117,7 +128,7 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
         yolat_bn bn2 = dry ? yolat_bn{} : p->bn2;
         YOLAT_TRY(linear_bn_stats(a, ws, &bn2, training, t.stat2, st));
       }
-      if (!dry) YOLAT_TRY(edge_agg(g, N, C, t.z2, t.stat2, ew, out, ldo, st));
+      if (!dry) YOLAT_TRY(edge_agg(g, N, C, t.z2, t.stat2, ew, out, ldo, out, ldo, st));
     }
   }
   // ---- node path: mlp_node(x_node)  (torch_vertex.py:326) -----------------------------------------
@@ -235,7 +246,7 @@ static int gp2_bwd_impl(const yolat_gp2_params* p, const yolat_gp2_grads* gr, in
       if (!dry && G.w1) YOLAT_TRY(edge_assemble_dw1(dwpq, dw1c, Cin, C, G.w1, st));
     }
     if (dx || dry) {     // dx += dPQ Wpq
-      if (!dry) YOLAT_TRY(edge_prep_wpq(p->w1, Cin, C, wpq, st));
+      if (!dry) YOLAT_TRY(edge_prep_wpq(p->w1, Cin, C, wpq, nullptr, nullptr, nullptr, st));
       GemmArgs a{};
       a.A = dpq; a.lda = 2 * C; a.B = wpq; a.ldb = Cin; a.C = dx; a.ldc = lddx;
       a.M = (int)N; a.N = Cin; a.K = 2 * C; a.accumulate = acc_dx;

@@ -35,8 +35,10 @@ __device__ __forceinline__ void stv(float* p, const float (&v)[CPL]) {
   *reinterpret_cast<V*>(p) = t;
 }
 
-// Wpq [2C, Cin]: rows 0..C-1 = W1a - W1b, rows C..2C-1 = W1b
-__global__ void k_prep_wpq(const float* __restrict__ w1, int Cin, int C, float* __restrict__ wpq) {
+// Wpq [2C, Cin]: rows 0..C-1 = W1a - W1b, rows C..2C-1 = W1b.  With wr != null also rows 2C..3C-1 = Wr (lin_r) and
+// bias3 [3C] = (0, 0, br): one GEMM then produces P | Q | lin_r(x).
+__global__ void k_prep_wpq(const float* __restrict__ w1, int Cin, int C, float* __restrict__ wpq,
+                           const float* __restrict__ wr, const float* __restrict__ br, float* __restrict__ bias3) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= C * Cin) return;
   const int c = idx / Cin, k = idx % Cin;
@@ -44,6 +46,14 @@ __global__ void k_prep_wpq(const float* __restrict__ w1, int Cin, int C, float* 
   const float a = w1[c * ld + k], b = w1[c * ld + Cin + k];
   wpq[c * Cin + k] = a - b;
   wpq[(C + c) * Cin + k] = b;
+  if (wr) {
+    wpq[(2 * C + c) * Cin + k] = wr[c * Cin + k];
+    if (k == 0) {
+      bias3[c] = 0.f;
+      bias3[C + c] = 0.f;
+      bias3[2 * C + c] = br ? br[c] : 0.f;
+    }
+  }
 }
 
 // dW1 [C, 2Cin+4] from dWpq [2C, Cin] and dW1c [C,4]:  dW1a = dWp, dW1b = dWq - dWp
@@ -120,11 +130,11 @@ k_edge_z1(GraphView g, int64_t N, const float* __restrict__ pq, const float* __r
   }
 }
 
-// out[v] += deg_inv[v] * sum_{slot in row v} relu(bn2(z2[slot])) (* edge_weight[eid])
+// out[v] = base[v] + deg_inv[v] * sum_{slot in row v} relu(bn2(z2[slot])) (* edge_weight[eid]); base may alias out
 template <int CPL>
 __global__ void __launch_bounds__(EDGE_WARPS * 32)
 k_edge_agg(GraphView g, int64_t N, const float* __restrict__ z2, const float* __restrict__ stat2,
-           const float* __restrict__ ew, float* __restrict__ out, int64_t ldo) {
+           const float* __restrict__ ew, const float* base, int64_t ldb, float* out, int64_t ldo) {
   constexpr int C = 32 * CPL;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int c0 = lane * CPL;
@@ -133,7 +143,7 @@ k_edge_agg(GraphView g, int64_t N, const float* __restrict__ z2, const float* __
   for (int q = 0; q < CPL; ++q) { sc[q] = stat2[c0 + q]; sh[q] = stat2[C + c0 + q]; }
   for (int64_t row = (int64_t)blockIdx.x * EDGE_WARPS + wid; row < N; row += (int64_t)gridDim.x * EDGE_WARPS) {
     const int b = g.rowptr_t[row], e = g.rowptr_t[row + 1];
-    if (b == e) continue;
+    if (b == e && base == out) continue;
     float acc[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) acc[q] = 0.f;
@@ -145,9 +155,11 @@ k_edge_agg(GraphView g, int64_t N, const float* __restrict__ z2, const float* __
       for (int q = 0; q < CPL; ++q) acc[q] += wgt * fmaxf(fmaf(z[q], sc[q], sh[q]), 0.f);
     }
     const float di = g.deg_inv[row];
-    float* o = out + row * ldo + c0;
+    float bv[CPL];
+    ldv<CPL>(base + row * ldb + c0, bv);
 #pragma unroll
-    for (int q = 0; q < CPL; ++q) o[q] += acc[q] * di;
+    for (int q = 0; q < CPL; ++q) bv[q] += acc[q] * di;
+    stv<CPL>(out + row * ldo + c0, bv);
   }
 }
 
@@ -227,8 +239,9 @@ static int edge_grid(int64_t N) {
   return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
-int edge_prep_wpq(const float* w1, int Cin, int C, float* wpq, cudaStream_t st) {
-  k_prep_wpq<<<(unsigned)cdiv(C * Cin, 256), 256, 0, st>>>(w1, Cin, C, wpq);
+int edge_prep_wpq(const float* w1, int Cin, int C, float* wpq, const float* wr, const float* br, float* bias3,
+                  cudaStream_t st) {
+  k_prep_wpq<<<(unsigned)cdiv(C * Cin, 256), 256, 0, st>>>(w1, Cin, C, wpq, wr, br, bias3);
   YOLAT_CHECK_LAUNCH();
   return YOLAT_OK;
 }
@@ -254,13 +267,13 @@ int edge_z1(const GraphView& g, int64_t N, int C, const float* pq, const float* 
   return YOLAT_OK;
 }
 
-int edge_agg(const GraphView& g, int64_t N, int C, const float* z2, const float* stat2, const float* ew, float* out,
-             int64_t ldo, cudaStream_t st) {
+int edge_agg(const GraphView& g, int64_t N, int C, const float* z2, const float* stat2, const float* ew,
+             const float* base, int64_t ldb, float* out, int64_t ldo, cudaStream_t st) {
   const int grid = edge_grid(N);
   switch (C) {
-    case 32: k_edge_agg<1><<<grid, EDGE_WARPS * 32, 0, st>>>(g, N, z2, stat2, ew, out, ldo); break;
-    case 64: k_edge_agg<2><<<grid, EDGE_WARPS * 32, 0, st>>>(g, N, z2, stat2, ew, out, ldo); break;
-    case 128: k_edge_agg<4><<<grid, EDGE_WARPS * 32, 0, st>>>(g, N, z2, stat2, ew, out, ldo); break;
+    case 32: k_edge_agg<1><<<grid, EDGE_WARPS * 32, 0, st>>>(g, N, z2, stat2, ew, base, ldb, out, ldo); break;
+    case 64: k_edge_agg<2><<<grid, EDGE_WARPS * 32, 0, st>>>(g, N, z2, stat2, ew, base, ldb, out, ldo); break;
+    case 128: k_edge_agg<4><<<grid, EDGE_WARPS * 32, 0, st>>>(g, N, z2, stat2, ew, base, ldb, out, ldo); break;
     default: return YOLAT_ERR_UNSUPPORTED;
   }
   YOLAT_CHECK_LAUNCH();

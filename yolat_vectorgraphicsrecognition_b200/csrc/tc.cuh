@@ -32,6 +32,33 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
   }
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+// named barrier among `nthreads` threads (multiple of 32) of the CTA; id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// Long waits (a whole pipeline stage): back off with nanosleep so the spinning warp does not steal issue slots
+// from the warps doing the work.  Same bounded-time trap as mbar_wait.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t addr, uint32_t parity) {
+  if (mbar_try_wait(addr, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(addr, parity)) {
+    __nanosleep(40);
+    if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
+  }
+}
+// one lane of a fully converged warp; keeps the guarded region in the uniform datapath (descriptors in UR registers)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -97,6 +124,21 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
   hi = __uint_as_float(h);
   lo = x - hi;
+}
+// Same split for finite inputs in 2 + 1 instructions per value (cvt.rna.tf32 compiles to 4): adding half an ulp of
+// the 10-bit mantissa and masking the low 13 bits is round-to-nearest, ties away from zero, on the magnitude.
+__device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
+}
+__device__ __forceinline__ void store_split_fast(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, const float4& v) {
+  float4 h, l;
+  split_tf32_fast(v.x, h.x, l.x);
+  split_tf32_fast(v.y, h.y, l.y);
+  split_tf32_fast(v.z, h.z, l.z);
+  split_tf32_fast(v.w, h.w, l.w);
+  *reinterpret_cast<float4*>(hi_base + off) = h;
+  *reinterpret_cast<float4*>(lo_base + off) = l;
 }
 __device__ __forceinline__ void store_split(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, const float4& v) {
   float4 h, l;
