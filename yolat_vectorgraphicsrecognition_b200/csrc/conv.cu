@@ -40,6 +40,47 @@ static bool gemm_fused_enabled() {
   return v == 1;
 }
 
+// ---- branch concurrency ------------------------------------------------------------------------------------------
+// The edge path, the lin_r product and the node branch of one GraphConv are independent until the very end, and at
+// config-2 sizes most of their kernels are too small to fill 148 SMs.  They run on two library-owned side streams,
+// forked from / joined back into the caller's stream with events; stream-ordered and capturable, so inside a CUDA
+// graph the branches become parallel paths.  YOLAT_BRANCHES=0 runs everything on the caller's stream.
+struct Branches {
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  bool ok = false;
+};
+static Branches* branches() {
+  static thread_local Branches b[16];
+  static const bool enabled = !(getenv("YOLAT_BRANCHES") && getenv("YOLAT_BRANCHES")[0] == '0');
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  Branches& r = b[dev];
+  if (!r.ok) {
+    bool good = true;
+    for (int i = 0; i < 2; ++i) {
+      good = good && cudaStreamCreateWithFlags(&r.side[i], cudaStreamNonBlocking) == cudaSuccess;
+      good = good && cudaEventCreateWithFlags(&r.join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    good = good && cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming) == cudaSuccess;
+    if (!good) return nullptr;
+    r.ok = true;
+  }
+  return &r;
+}
+// side streams start after everything already enqueued on `st`
+static void fork_branches(Branches* b, cudaStream_t st) {
+  cudaEventRecord(b->fork, st);
+  cudaStreamWaitEvent(b->side[0], b->fork, 0);
+  cudaStreamWaitEvent(b->side[1], b->fork, 0);
+}
+// `st` continues after everything enqueued so far on side stream i
+static void join_branch(Branches* b, int i, cudaStream_t st) {
+  cudaEventRecord(b->join[i], b->side[i]);
+  cudaStreamWaitEvent(st, b->join[i], 0);
+}
+
 static bool gp2_channels_ok(int Cin, int Cn, int C) {
   return (C == 32 || C == 64 || C == 128) && Cin >= 1 && Cn >= 1;
 }
@@ -70,13 +111,25 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
 
   GraphView g;
   if (!dry) graph_layout(N, E, graph, &g);
+  Branches* br = dry ? nullptr : branches();
+  cudaStream_t st_node = br ? br->side[0] : st, st_linr = br ? br->side[1] : st;
+  if (br) fork_branches(br, st);
 
   // ---- lin_r: out = x Wr^T + br  (torch_vertex.py:325) ------------------------------------------
   if (!pqr) {
     GemmArgs a{};
     a.A = x; a.lda = ldx; a.B = dry ? nullptr : p->wr; a.ldb = Cin; a.C = out; a.ldc = ldo;
     a.M = (int)N; a.N = C; a.K = Cin; a.bias = dry ? nullptr : p->br;
-    YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
+    YOLAT_TRY(gemm(a, GEMM_NT, ws, st_linr));
+  }
+  // ---- node path: mlp_node(x_node)  (torch_vertex.py:326) -----------------------------------------
+  {
+    GemmArgs a{};
+    a.A = x_node; a.lda = ldxn; a.B = dry ? nullptr : p->wn; a.ldb = Cn; a.C = t.zn; a.ldc = C;
+    a.M = (int)N; a.N = C; a.K = Cn; a.bias = dry ? nullptr : p->bnode;
+    yolat_bn bnn = dry ? yolat_bn{} : p->bnn;
+    YOLAT_TRY(linear_bn_stats(a, ws, &bnn, training, t.statn, st_node));
+    if (!dry) YOLAT_TRY(bn_apply(t.zn, C, N, C, t.statn, 1, xnode_out, ldxo, st_node));
   }
   // ---- edge path ---------------------------------------------------------------------------------
   if (E > 0) {
@@ -103,6 +156,7 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
           YOLAT_TRY(edge_fused(g, N, E, EF_STATS | (no_tape ? 0 : EF_TAPE), pq, ldpq, attr, p->w1, Cin, p->b1, t.stat1,
                                p->w2, p->b2, nullptr, ew, t.z1, t.z2, part2, nullptr, 0, nullptr, 0, st));
           YOLAT_TRY(bn_finalize_from_partials(part2, ngrid, E, C, &p->bn2, 1, t.stat2, st));
+          if (br) join_branch(br, 1, st);      // lin_r(x) must be in `out` before the aggregation adds to it
           if (no_tape) {
             YOLAT_TRY(edge_fused(g, N, E, EF_AGG, pq, ldpq, attr, p->w1, Cin, p->b1, t.stat1, p->w2, p->b2, t.stat2, ew,
                                  nullptr, nullptr, nullptr, base, ldbase, out, ldo, st));
@@ -111,6 +165,7 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
           }
         } else {
           YOLAT_TRY(bn_finalize_from_partials(nullptr, 0, E, C, &p->bn2, 0, t.stat2, st));
+          if (br) join_branch(br, 1, st);
           YOLAT_TRY(edge_fused(g, N, E, EF_AGG | (no_tape ? 0 : EF_TAPE), pq, ldpq, attr, p->w1, Cin, p->b1, t.stat1,
                                p->w2, p->b2, t.stat2, ew, t.z1, t.z2, nullptr, base, ldbase, out, ldo, st));
         }
@@ -128,18 +183,13 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
         yolat_bn bn2 = dry ? yolat_bn{} : p->bn2;
         YOLAT_TRY(linear_bn_stats(a, ws, &bn2, training, t.stat2, st));
       }
+      if (br) join_branch(br, 1, st);
       if (!dry) YOLAT_TRY(edge_agg(g, N, C, t.z2, t.stat2, ew, out, ldo, out, ldo, st));
     }
+  } else if (br) {
+    join_branch(br, 1, st);
   }
-  // ---- node path: mlp_node(x_node)  (torch_vertex.py:326) -----------------------------------------
-  {
-    GemmArgs a{};
-    a.A = x_node; a.lda = ldxn; a.B = dry ? nullptr : p->wn; a.ldb = Cn; a.C = t.zn; a.ldc = C;
-    a.M = (int)N; a.N = C; a.K = Cn; a.bias = dry ? nullptr : p->bnode;
-    yolat_bn bnn = dry ? yolat_bn{} : p->bnn;
-    YOLAT_TRY(linear_bn_stats(a, ws, &bnn, training, t.statn, st));
-    if (!dry) YOLAT_TRY(bn_apply(t.zn, C, N, C, t.statn, 1, xnode_out, ldxo, st));
-  }
+  if (br) join_branch(br, 0, st);
   if (!dry && ws.overflow) return YOLAT_ERR_WORKSPACE;
   return YOLAT_OK;
 }
@@ -160,41 +210,44 @@ static int gp2_bwd_impl(const yolat_gp2_params* p, const yolat_gp2_grads* gr, in
   GraphView g;
   if (!dry) graph_layout(N, E, graph, &g);
   int acc_dx = accumulate_dx, acc_dxn = accumulate_dx;
+  Branches* br = dry ? nullptr : branches();
+  cudaStream_t st_node = br ? br->side[0] : st, st_linr = br ? br->side[1] : st;
+  if (br) fork_branches(br, st);
 
-  // ---- node branch -------------------------------------------------------------------------------
+  // ---- node branch (side stream 0) -----------------------------------------------------------------
   {
     float* dzn = ws.take(N * C);
     BnBwdArgs b{};
     b.gy = g_xnode; b.ldgy = ldgx; b.z = t.zn; b.ldz = C; b.M = N; b.C = C; b.stat = t.statn;
     b.gamma = dry ? nullptr : p->bnn.w; b.relu = 1; b.training = training; b.dz = dzn; b.lddz = C;
     b.dgamma = G.bnn_w; b.dbeta = G.bnn_b; b.dbias = G.bnode;
-    YOLAT_TRY(bn_backward(b, ws, st));
+    YOLAT_TRY(bn_backward(b, ws, st_node));
     if (G.wn || dry) {
       GemmArgs a{};
       a.A = dzn; a.lda = C; a.B = x_node; a.ldb = ldxn; a.C = G.wn; a.ldc = Cn; a.M = C; a.N = Cn; a.K = N;
-      YOLAT_TRY(gemm(a, GEMM_TN, ws, st));
+      YOLAT_TRY(gemm(a, GEMM_TN, ws, st_node));
     }
     if (dx_node || dry) {
       GemmArgs a{};
       a.A = dzn; a.lda = C; a.B = dry ? nullptr : p->wn; a.ldb = Cn; a.C = dx_node; a.ldc = lddxn;
       a.M = (int)N; a.N = Cn; a.K = C; a.accumulate = acc_dxn;
-      YOLAT_TRY(gemm(a, GEMM_NN, ws, st));
+      YOLAT_TRY(gemm(a, GEMM_NN, ws, st_node));
       acc_dxn = 1;
     }
   }
 
-  // ---- lin_r --------------------------------------------------------------------------------------
+  // ---- lin_r (side stream 1) ------------------------------------------------------------------------
   if (G.wr || dry) {
     GemmArgs a{};
     a.A = g_out; a.lda = ldgo; a.B = x; a.ldb = ldx; a.C = G.wr; a.ldc = Cin; a.M = C; a.N = Cin; a.K = N;
-    YOLAT_TRY(gemm(a, GEMM_TN, ws, st));
+    YOLAT_TRY(gemm(a, GEMM_TN, ws, st_linr));
   }
-  if (G.br || dry) YOLAT_TRY(colsum(g_out, ldgo, N, C, G.br, ws, st));
+  if (G.br || dry) YOLAT_TRY(colsum(g_out, ldgo, N, C, G.br, ws, st_linr));
   if (dx || dry) {
     GemmArgs a{};
     a.A = g_out; a.lda = ldgo; a.B = dry ? nullptr : p->wr; a.ldb = Cin; a.C = dx; a.ldc = lddx;
     a.M = (int)N; a.N = Cin; a.K = C; a.accumulate = acc_dx;
-    YOLAT_TRY(gemm(a, GEMM_NN, ws, st));
+    YOLAT_TRY(gemm(a, GEMM_NN, ws, st_linr));
     acc_dx = 1;
   }
 
@@ -245,7 +298,8 @@ static int gp2_bwd_impl(const yolat_gp2_params* p, const yolat_gp2_grads* gr, in
       YOLAT_TRY(gemm(a, GEMM_TN, ws, st));
       if (!dry && G.w1) YOLAT_TRY(edge_assemble_dw1(dwpq, dw1c, Cin, C, G.w1, st));
     }
-    if (dx || dry) {     // dx += dPQ Wpq
+    if (dx || dry) {     // dx += dPQ Wpq  (after lin_r's own contribution to dx)
+      if (br) join_branch(br, 1, st);
       if (!dry) YOLAT_TRY(edge_prep_wpq(p->w1, Cin, C, wpq, nullptr, nullptr, nullptr, st));
       GemmArgs a{};
       a.A = dpq; a.lda = 2 * C; a.B = wpq; a.ldb = Cin; a.C = dx; a.ldc = lddx;
@@ -257,6 +311,10 @@ static int gp2_bwd_impl(const yolat_gp2_params* p, const yolat_gp2_grads* gr, in
     YOLAT_TRY(zero_opt(G.bn1_w, C, st)); YOLAT_TRY(zero_opt(G.bn1_b, C, st));
     YOLAT_TRY(zero_opt(G.w2, (int64_t)C * C, st)); YOLAT_TRY(zero_opt(G.b2, C, st));
     YOLAT_TRY(zero_opt(G.bn2_w, C, st)); YOLAT_TRY(zero_opt(G.bn2_b, C, st));
+  }
+  if (br) {
+    join_branch(br, 1, st);
+    join_branch(br, 0, st);
   }
   if (!dry && ws.overflow) return YOLAT_ERR_WORKSPACE;
   return YOLAT_OK;

@@ -93,6 +93,48 @@ struct KMajor {
       store_split(hi, lo, off, v[i]);
     }
   }
+  // Fast path (16-byte aligned operand, K % 4 == 0): unconditional vector loads from clamped addresses -- no branch
+  // between the load and its first use, so the loads really stay in flight until stash_fast() two k-blocks later.
+  // Out-of-range chunks are zeroed and the BN+ReLU prologue is applied at stash time.
+  uint32_t ok;
+  __device__ __forceinline__ void fetch_fast(const float* __restrict__ base, int64_t ld, int row0, int rows_total,
+                                             int64_t k0, int64_t k_end) {
+    const int t = threadIdx.x, c = t & 7;
+    const int64_t k = k0 + c * 4;
+    const bool kin = k < k_end;
+    const int64_t kc = kin ? k : k0;
+    ok = 0;
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; ++i) {
+      const int row = row0 + (t >> 3) + 32 * i;
+      const bool in = kin && row < rows_total;
+      const int rc = row < rows_total ? row : rows_total - 1;
+      v[i] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)rc * ld + kc));
+      ok |= in ? (1u << i) : 0u;
+    }
+  }
+  __device__ __forceinline__ void stash_fast(uint8_t* hi, uint8_t* lo, int64_t k0, const float* __restrict__ sc,
+                                             const float* __restrict__ sh) const {
+    const int t = threadIdx.x, c = t & 7;
+    float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sc && ok) {      // per reduction index k (uniform branch on sc; ok != 0 implies k in range)
+      const int64_t k = k0 + c * 4;
+      s4 = make_float4(__ldg(sc + k), __ldg(sc + k + 1), __ldg(sc + k + 2), __ldg(sc + k + 3));
+      h4 = make_float4(__ldg(sh + k), __ldg(sh + k + 1), __ldg(sh + k + 2), __ldg(sh + k + 3));
+    }
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; ++i) {
+      const int row = (t >> 3) + 32 * i;
+      float4 x = v[i];
+      if (sc) {
+        x.x = fmaxf(fmaf(x.x, s4.x, h4.x), 0.f); x.y = fmaxf(fmaf(x.y, s4.y, h4.y), 0.f);
+        x.z = fmaxf(fmaf(x.z, s4.z, h4.z), 0.f); x.w = fmaxf(fmaf(x.w, s4.w, h4.w), 0.f);
+      }
+      if (!((ok >> i) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+      store_split_fast(hi, lo, off, x);
+    }
+  }
 };
 
 // MN-major operand: element (mn, k) at base[k*ld + mn].  MN x 32 tile; one 128-byte smem row holds 32
@@ -152,6 +194,49 @@ struct MNMajor {
       const uint32_t off = (uint32_t)(kr >> 2) * (uint32_t)(MN / 32 * 512) + (uint32_t)(cm >> 3) * 512u +
                            (uint32_t)kr4 * 128u + (uint32_t)((((c16 >> 1) ^ kr4) << 5) | ((c16 & 1) << 4));
       store_split(hi, lo, off, v[i]);
+    }
+  }
+  // Fast path: see KMajor::fetch_fast (requires mn_total % 4 == 0 and a 16-byte aligned operand).
+  uint32_t ok;
+  __device__ __forceinline__ void fetch_fast(const float* __restrict__ base, int64_t ld, int mn0, int mn_total,
+                                             int64_t k0, int64_t k_end) {
+    const int t = threadIdx.x, cm = t % CPR;
+    const int mn = mn0 + cm * 4;
+    const bool min_ = mn < mn_total;
+    const int mnc = min_ ? mn : 0;
+    ok = 0;
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; ++i) {
+      const int64_t k = k0 + t / CPR + KR_PER_PASS * i;
+      const bool in = min_ && k < k_end;
+      const int64_t kc = k < k_end ? k : k0;
+      v[i] = __ldg(reinterpret_cast<const float4*>(base + kc * ld + mnc));
+      ok |= in ? (1u << i) : 0u;
+    }
+  }
+  __device__ __forceinline__ void stash_fast(uint8_t* hi, uint8_t* lo, int mn0, const float* __restrict__ sc,
+                                             const float* __restrict__ sh) const {
+    const int t = threadIdx.x, cm = t % CPR;
+    const int c16 = cm & 7;
+    float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sc && ok) {      // per output index mn
+      const int mn = mn0 + cm * 4;
+      s4 = make_float4(__ldg(sc + mn), __ldg(sc + mn + 1), __ldg(sc + mn + 2), __ldg(sc + mn + 3));
+      h4 = make_float4(__ldg(sh + mn), __ldg(sh + mn + 1), __ldg(sh + mn + 2), __ldg(sh + mn + 3));
+    }
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; ++i) {
+      const int kr = t / CPR + KR_PER_PASS * i;
+      const int kr4 = kr & 3;
+      float4 x = v[i];
+      if (sc) {
+        x.x = fmaxf(fmaf(x.x, s4.x, h4.x), 0.f); x.y = fmaxf(fmaf(x.y, s4.y, h4.y), 0.f);
+        x.z = fmaxf(fmaf(x.z, s4.z, h4.z), 0.f); x.w = fmaxf(fmaf(x.w, s4.w, h4.w), 0.f);
+      }
+      if (!((ok >> i) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint32_t off = (uint32_t)(kr >> 2) * (uint32_t)(MN / 32 * 512) + (uint32_t)(cm >> 3) * 512u +
+                           (uint32_t)kr4 * 128u + (uint32_t)((((c16 >> 1) ^ kr4) << 5) | ((c16 & 1) << 4));
+      store_split_fast(hi, lo, off, x);
     }
   }
 };
@@ -218,8 +303,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const Params p) {
     if (kb + STAGES < nkb) fetch(kb + STAGES, ra, rb);
     fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the tensor core
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
+      if (elect_one_sync()) {   // converged warp, one elected lane: descriptors stay in uniform registers
       const uint32_t sa = tiles_u32 + (uint32_t)s * STAGE_BYTES;
       const uint32_t sb = sa + 2 * A_BYTES;
 #pragma unroll
@@ -240,6 +326,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const Params p) {
       }
       umma_commit(smem_u32(&mbar_empty[s]));
       if (kb + 1 == nkb) umma_commit(smem_u32(&mbar_done));
+      }
+      __syncwarp();
     }
   };
 
@@ -344,6 +432,281 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const Params p) {
   if (warp == 0) tmem_dealloc(tmem_d, BN);
 }
 
+// ---- persistent, warp-specialised variant ---------------------------------------------------------------------------
+// One CTA per SM walks the (n-tile, m-tile, k-split) list round-robin.  Roles, connected by mbarriers only:
+//   warps 0..7  producers: global -> registers (2 k-blocks in flight) -> BN+ReLU prologue -> 3xTF32 split -> smem ring
+//               (3 stages of 64 KB for BN = 128, 4 stages of 48 KB for BN = 64); they run ahead across tile boundaries;
+//   warp  8     MMA issue: one elected lane, 12 tcgen05.mma per k-block into one of two TMEM accumulators;
+//   warps 9..12 epilogue: tcgen05.ld (lane quarter = warp & 3) -> bias / accumulate -> direct 128-byte row stores, or
+//               split-K partial tiles; per-warp column statistics through a private 32 x 33 transpose tile.
+// The epilogue of tile i overlaps the main loop of tile i+1, which the one-tile-per-CTA kernel above cannot do.
+constexpr int WS_PRODUCERS = 8, WS_THREADS = (WS_PRODUCERS + 1 + 4) * 32;
+template <int BN> struct WsCfg {
+  static constexpr int NST = (BN == 128) ? 3 : 4;
+  static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * BN * 128;
+  static constexpr uint32_t XPOSE_BYTES = 4 * 32 * 33 * 4;
+  static constexpr size_t SMEM = (size_t)NST * STAGE_BYTES + XPOSE_BYTES + 1024;
+};
+
+template <int MODE, int BN, bool FAST>
+__global__ void __launch_bounds__(WS_THREADS, 1) k_tc_gemm_ws(const Params p, const int gn, const int gm, const int ksplit) {
+  using Cfg = WsCfg<BN>;
+  constexpr int NST = Cfg::NST;
+  constexpr uint32_t B_BYTES = BN * 128;
+  constexpr uint32_t STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr bool A_MN = (MODE == GEMM_TN);
+  constexpr bool B_MN = (MODE != GEMM_NT);
+  constexpr uint32_t IDESC = make_idesc(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[NST], bar_empty[NST], bar_acc_full[2], bar_acc_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_u32 + 1023u) & ~1023u) - raw_u32;
+  uint8_t* tiles = smem_raw + pad;
+  const uint32_t tiles_u32 = raw_u32 + pad;
+  float* xpose = reinterpret_cast<float*>(tiles + NST * STAGE_BYTES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total = gn * gm * ksplit;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(smem_u32(&bar_full[i]), WS_PRODUCERS * 32);
+      mbar_init(smem_u32(&bar_empty[i]), 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_acc_full[i]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[i]), 4 * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == WS_PRODUCERS) tmem_alloc(smem_u32(&tmem_base_slot), 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_slot;
+
+  // tile id -> (n-tile fastest: neighbouring CTAs share their A rows in L2)
+  struct Cur { int tile, kb, nkb, m0, n0, z; int64_t kbeg, kend; };
+  auto load_tile = [&](int tile, Cur& c) {
+    c.tile = tile; c.kb = 0; c.nkb = 0;
+    if (tile >= total) return;
+    const int nx = tile % gn, rest = tile / gn;
+    c.n0 = nx * BN; c.m0 = (rest % gm) * BM; c.z = rest / gm;
+    c.kbeg = (int64_t)c.z * p.k_chunk;
+    c.kend = min(p.K, c.kbeg + p.k_chunk);
+    c.nkb = (int)((c.kend - c.kbeg + BK - 1) / BK);
+  };
+
+  if (warp < WS_PRODUCERS) {
+    // =========================== producers ===============================================================
+    typename Loaders<MODE, BN>::ALoad la[2];
+    typename Loaders<MODE, BN>::BLoad lb[2];
+    Cur f, s;
+    load_tile(blockIdx.x, f);
+    s = f;
+    auto next = [&](Cur& c) { if (++c.kb >= c.nkb) load_tile(c.tile + gridDim.x, c); };
+    auto fetch = [&](Cur& c, typename Loaders<MODE, BN>::ALoad& ra, typename Loaders<MODE, BN>::BLoad& rb) {
+      if (c.tile >= total) return;
+      const int64_t k0 = c.kbeg + (int64_t)c.kb * BK;
+      if (FAST) {
+        ra.fetch_fast(p.A, p.lda, c.m0, p.M, k0, c.kend);
+        rb.fetch_fast(p.B, p.ldb, c.n0, p.N, k0, c.kend);
+      } else {
+        ra.fetch(p.A, p.lda, c.m0, p.M, k0, c.kend, p.a_vec, p.a_sc, p.a_sh);
+        rb.fetch(p.B, p.ldb, c.n0, p.N, k0, c.kend, p.b_vec, MODE == GEMM_TN ? p.b_sc : nullptr, p.b_sh);
+      }
+      next(c);
+    };
+    fetch(f, la[0], lb[0]);
+    fetch(f, la[1], lb[1]);
+    int st = 0;
+    uint32_t use = 0;     // how many times the ring has wrapped
+    auto step = [&](typename Loaders<MODE, BN>::ALoad& ra, typename Loaders<MODE, BN>::BLoad& rb) {
+      if (use > 0) mbar_wait(smem_u32(&bar_empty[st]), (use - 1) & 1u);     // the MMAs that read this stage are done
+      uint8_t* sp = tiles + (uint32_t)st * STAGE_BYTES;
+      if (FAST) {
+        const int64_t k0 = s.kbeg + (int64_t)s.kb * BK;
+        // K-major operands carry the prologue per k, MN-major ones per m / n
+        if (MODE == GEMM_TN) ra.stash_fast(sp, sp + A_BYTES, s.m0, p.a_sc, p.a_sh);
+        else ra.stash_fast(sp, sp + A_BYTES, k0, p.a_sc, p.a_sh);
+        if (MODE == GEMM_NT) rb.stash_fast(sp + 2 * A_BYTES, sp + 2 * A_BYTES + B_BYTES, k0, nullptr, nullptr);
+        else rb.stash_fast(sp + 2 * A_BYTES, sp + 2 * A_BYTES + B_BYTES, s.n0, MODE == GEMM_TN ? p.b_sc : nullptr, p.b_sh);
+      } else {
+        ra.stash(sp, sp + A_BYTES);
+        rb.stash(sp + 2 * A_BYTES, sp + 2 * A_BYTES + B_BYTES);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&bar_full[st]));
+      fetch(f, ra, rb);
+      if (++st == NST) { st = 0; ++use; }
+      next(s);
+    };
+    while (s.tile < total) {
+      step(la[0], lb[0]);
+      if (s.tile >= total) break;
+      step(la[1], lb[1]);
+    }
+  } else if (warp == WS_PRODUCERS) {
+    // =========================== MMA issue ===============================================================
+    int st = 0;
+    uint32_t use = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      Cur c;
+      load_tile(tile, c);
+      const int a = it & 1;
+      if (it >= 2) mbar_wait(smem_u32(&bar_acc_empty[a]), (uint32_t)(((it >> 1) - 1) & 1));
+      const uint32_t d = tmem_d + (uint32_t)(a * BN);
+      for (int kb = 0; kb < c.nkb; ++kb) {
+        mbar_wait(smem_u32(&bar_full[st]), use & 1u);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t sa = tiles_u32 + (uint32_t)st * STAGE_BYTES;
+          const uint32_t sb = sa + 2 * A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint32_t a_off = A_MN ? (uint32_t)ks * (BM / 32 * 1024) : (uint32_t)ks * 32u;
+            const uint32_t b_off = B_MN ? (uint32_t)ks * (BN / 32 * 1024) : (uint32_t)ks * 32u;
+            const uint64_t a_hi = A_MN ? make_desc(sa + a_off, 512, BM / 32 * 512, LAYOUT_SW128_BASE32B)
+                                       : make_desc(sa + a_off, 16, 1024, LAYOUT_SW128);
+            const uint64_t a_lo = A_MN ? make_desc(sa + A_BYTES + a_off, 512, BM / 32 * 512, LAYOUT_SW128_BASE32B)
+                                       : make_desc(sa + A_BYTES + a_off, 16, 1024, LAYOUT_SW128);
+            const uint64_t b_hi = B_MN ? make_desc(sb + b_off, 512, BN / 32 * 512, LAYOUT_SW128_BASE32B)
+                                       : make_desc(sb + b_off, 16, 1024, LAYOUT_SW128);
+            const uint64_t b_lo = B_MN ? make_desc(sb + B_BYTES + b_off, 512, BN / 32 * 512, LAYOUT_SW128_BASE32B)
+                                       : make_desc(sb + B_BYTES + b_off, 16, 1024, LAYOUT_SW128);
+            umma_tf32(d, a_lo, b_hi, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
+            umma_tf32(d, a_hi, b_lo, IDESC, 1u);
+            umma_tf32(d, a_hi, b_hi, IDESC, 1u);
+          }
+          umma_commit(smem_u32(&bar_empty[st]));
+          if (kb + 1 == c.nkb) umma_commit(smem_u32(&bar_acc_full[a]));
+        }
+        __syncwarp();
+        if (++st == NST) { st = 0; ++use; }
+      }
+    }
+  } else {
+    // =========================== epilogue ================================================================
+    const int q4 = warp & 3;                       // TMEM lane quarter this warp may read
+    float* xp = xpose + (warp - WS_PRODUCERS - 1) * (32 * 33);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      Cur c;
+      load_tile(tile, c);
+      const int a = it & 1;
+      mbar_wait_sleep(smem_u32(&bar_acc_full[a]), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const int row = c.m0 + q4 * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int rows_w = min(32, p.M - (c.m0 + q4 * 32));     // valid rows of this warp's quarter (may be <= 0)
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        float v[32];
+        tmem_ld32(tmem_d + (uint32_t)(a * BN + j * 32) + ((uint32_t)(q4 * 32) << 16), v);
+        if (j == BN / 32 - 1) {
+          tc_fence_before();
+          mbar_arrive(smem_u32(&bar_acc_empty[a]));           // the accumulator may be overwritten by tile it + 2
+        }
+        const int col0 = c.n0 + j * 32;
+        if (col0 >= p.N) continue;
+        const int cols = min(32, p.N - col0);
+        if (ksplit > 1) {
+          if (row_ok) {
+            float* o = p.part + ((int64_t)c.z * p.M + row) * p.N + col0;
+            if ((p.N & 3) == 0 && cols == 32) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < cols) o[i] = v[i];
+            }
+          }
+          continue;
+        }
+        if (p.bias) {
+          if (cols == 32 && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15u) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < cols) v[i] += __ldg(p.bias + col0 + i);
+          }
+        }
+        if (p.stat_part) {      // column statistics of z = acc + bias (before any accumulate: stats GEMMs never accumulate)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) xp[lane * 33 + i] = v[i];
+          __syncwarp();
+          float sm_ = 0.f, ss_ = 0.f;
+          for (int r = 0; r < rows_w; ++r) {
+            const float z = xp[r * 33 + lane];
+            sm_ += z;
+            ss_ = fmaf(z, z, ss_);
+          }
+          if (lane < cols) {
+            const int64_t pi = (int64_t)(c.m0 / BM) * 4 + q4;
+            p.stat_part[(pi * 2 + 0) * p.N + col0 + lane] = sm_;
+            p.stat_part[(pi * 2 + 1) * p.N + col0 + lane] = ss_;
+          }
+          __syncwarp();
+        }
+        if (row_ok) {
+          float* o = p.C + (int64_t)row * p.ldc + col0;
+          if (p.c_vec && cols == 32) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 w = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (p.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(o + i);
+                w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+              }
+              *reinterpret_cast<float4*>(o + i) = w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < cols) o[i] = p.accumulate ? o[i] + v[i] : v[i];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WS_PRODUCERS) tmem_dealloc(tmem_d, 2 * BN);
+}
+
+template <int MODE, int BN, bool FAST>
+static cudaError_t launch_ws2(const Params& p, int gn, int gm, int ksplit, cudaStream_t st) {
+  constexpr size_t smem = WsCfg<BN>::SMEM;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(k_tc_gemm_ws<MODE, BN, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int total = gn * gm * ksplit;
+  const int grid = total < kNumSMs ? total : kNumSMs;
+  k_tc_gemm_ws<MODE, BN, FAST><<<grid, WS_THREADS, smem, st>>>(p, gn, gm, ksplit);
+  return cudaSuccess;
+}
+template <int MODE, int BN>
+static cudaError_t launch_ws(const Params& p, int gn, int gm, int ksplit, cudaStream_t st) {
+  // fast loaders: aligned vector loads on both operands and no partial 16-byte chunk along the contiguous dimension
+  const bool a_k = (MODE != GEMM_TN), b_k = (MODE == GEMM_NT);      // operand contiguous along K?
+  const bool fast = p.a_vec && p.b_vec && ((a_k ? p.K : (int64_t)p.M) % 4 == 0) && ((b_k ? p.K : (int64_t)p.N) % 4 == 0);
+  return fast ? launch_ws2<MODE, BN, true>(p, gn, gm, ksplit, st) : launch_ws2<MODE, BN, false>(p, gn, gm, ksplit, st);
+}
+
 template <int MODE, int BN>
 static cudaError_t launch(const Params& p, dim3 grid, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (2 * A_BYTES + 2 * BN * 128) + 1024;
@@ -406,7 +769,7 @@ static int gemm_tc(const GemmArgs& a, GemmMode mode, Arena& ws, float* stat_part
   const TcPlan pl = tc_plan(a.M, a.N, a.K, mode, stat_nparts != nullptr);
   float* part = nullptr;
   if (pl.ksplit > 1) part = ws.take((int64_t)pl.ksplit * a.M * a.N);
-  if (stat_nparts) *stat_nparts = pl.ksplit > 1 ? 0 : pl.gm;
+  if (stat_nparts) *stat_nparts = pl.ksplit > 1 ? 0 : pl.gm * 4;    // one partial per epilogue warp (32 rows)
   if (ws.dry()) return YOLAT_OK;
   if (ws.overflow) return YOLAT_ERR_WORKSPACE;
   tc::Params p{};
@@ -423,9 +786,14 @@ static int gemm_tc(const GemmArgs& a, GemmMode mode, Arena& ws, float* stat_part
   dim3 grid(pl.gn, pl.gm, pl.ksplit);
   cudaError_t e = cudaSuccess;
   ProfScope prof(YOLAT_PROF_GEMM, st);
+  static const bool use_ws = !(getenv("YOLAT_TC_KERNEL") && getenv("YOLAT_TC_KERNEL")[0] == 'o');   // 'old' = one tile per CTA
 #define YOLAT_TC_CASE(MODE_)                                                    \
   case MODE_:                                                                   \
-    e = pl.bn == 128 ? tc::launch<MODE_, 128>(p, grid, st) : tc::launch<MODE_, 64>(p, grid, st); \
+    if (use_ws && a.K > 0)                                                      \
+      e = pl.bn == 128 ? tc::launch_ws<MODE_, 128>(p, pl.gn, pl.gm, pl.ksplit, st) \
+                       : tc::launch_ws<MODE_, 64>(p, pl.gn, pl.gm, pl.ksplit, st); \
+    else                                                                        \
+      e = pl.bn == 128 ? tc::launch<MODE_, 128>(p, grid, st) : tc::launch<MODE_, 64>(p, grid, st); \
     break;
   switch (mode) {
     YOLAT_TC_CASE(GEMM_NT)
@@ -513,7 +881,7 @@ int gemm_stats(const GemmArgs& a, GemmMode mode, Arena& ws, float** stat_part, i
   }
   float* sp = nullptr;
   if (stat_part) {
-    sp = ws.take((int64_t)cdiv(a.M, tc::BM) * 2 * a.N);
+    sp = ws.take((int64_t)cdiv(a.M, tc::BM) * 4 * 2 * a.N);
     *stat_part = sp;
   }
   return gemm_tc(a, mode, ws, sp, nparts, st);
