@@ -237,10 +237,13 @@ bool edge_fused_supported(int C);
 bool edge_fused_fits(int64_t N, int64_t ldpq);
 int edge_fused_grid(int64_t E);
 int edge_stats1_grid(int64_t E);
-int edge_stats1(const GraphView& g, int64_t N, int64_t E, const float* pq, int64_t ldpq, const float* attr,
+// slot-ordered records (P / Q byte offsets, eid | attribute row) of one layer call: the TMA-fed input of the kernels below
+int64_t edge_records_floats(int64_t E);
+int edge_records(const GraphView& g, int64_t E, const float* attr, int64_t ldpq, float* rec, cudaStream_t st);
+int edge_stats1(const GraphView& g, int64_t N, int64_t E, const float* pq, int64_t ldpq, const float* rec,
                 const float* w1, int Cin, const float* b1, float* part, cudaStream_t st);
 // EF_AGG: out = base + mean (base may alias out or be null); every row of out is written exactly once
-int edge_fused(const GraphView& g, int64_t N, int64_t E, int flags, const float* pq, int64_t ldpq, const float* attr,
+int edge_fused(const GraphView& g, int64_t N, int64_t E, int flags, const float* pq, int64_t ldpq, const float* rec,
                const float* w1, int Cin, const float* b1, const float* stat1, const float* w2, const float* b2,
                const float* stat2, const float* ew, float* z1, float* z2, float* part, const float* base, int64_t ldb,
                float* out, int64_t ldo, cudaStream_t st);

@@ -50,6 +50,9 @@ struct Branches {
   cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
   bool ok = false;
 };
+// Past this many nodes every kernel of a layer fills the GPU on its own and concurrent branches only fight over SMs and
+// L2 (measured at N = 320 000: the P | Q / lin_r / node GEMMs 108 -> 82 us each, pass A of K-EDGE 146 -> 81 us).
+constexpr int64_t kBranchMaxNodes = 65536;
 static Branches* branches() {
   static thread_local Branches b[16];
   static const bool enabled = !(getenv("YOLAT_BRANCHES") && getenv("YOLAT_BRANCHES")[0] == '0');
@@ -111,7 +114,7 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
 
   GraphView g;
   if (!dry) graph_layout(N, E, graph, &g);
-  Branches* br = dry ? nullptr : branches();
+  Branches* br = (dry || N > kBranchMaxNodes) ? nullptr : branches();
   cudaStream_t st_node = br ? br->side[0] : st, st_linr = br ? br->side[1] : st;
   if (br) fork_branches(br, st);
 
@@ -146,19 +149,21 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
       const int ngrid = edge_fused_grid(E), ngrid1 = edge_stats1_grid(E);
       float* part2 = ws.take((int64_t)ngrid * 2 * C);
       float* part1f = ws.take((int64_t)ngrid1 * 2 * C);
+      float* rec = ws.take(edge_records_floats(E));
       const float* base = pqr ? pq + 2 * C : out;       // lin_r(x): third column block, or already in `out`
       const int64_t ldbase = pqr ? ldpq : ldo;
       if (!dry) {
         if (ws.overflow) return YOLAT_ERR_WORKSPACE;
-        if (training) YOLAT_TRY(edge_stats1(g, N, E, pq, ldpq, attr, p->w1, Cin, p->b1, part1f, st));
+        YOLAT_TRY(edge_records(g, E, attr, ldpq, rec, st));
+        if (training) YOLAT_TRY(edge_stats1(g, N, E, pq, ldpq, rec, p->w1, Cin, p->b1, part1f, st));
         YOLAT_TRY(bn_finalize_from_partials(part1f, ngrid1, E, C, &p->bn1, training, t.stat1, st));
         if (training) {
-          YOLAT_TRY(edge_fused(g, N, E, EF_STATS | (no_tape ? 0 : EF_TAPE), pq, ldpq, attr, p->w1, Cin, p->b1, t.stat1,
+          YOLAT_TRY(edge_fused(g, N, E, EF_STATS | (no_tape ? 0 : EF_TAPE), pq, ldpq, rec, p->w1, Cin, p->b1, t.stat1,
                                p->w2, p->b2, nullptr, ew, t.z1, t.z2, part2, nullptr, 0, nullptr, 0, st));
           YOLAT_TRY(bn_finalize_from_partials(part2, ngrid, E, C, &p->bn2, 1, t.stat2, st));
           if (br) join_branch(br, 1, st);      // lin_r(x) must be in `out` before the aggregation adds to it
           if (no_tape) {
-            YOLAT_TRY(edge_fused(g, N, E, EF_AGG, pq, ldpq, attr, p->w1, Cin, p->b1, t.stat1, p->w2, p->b2, t.stat2, ew,
+            YOLAT_TRY(edge_fused(g, N, E, EF_AGG, pq, ldpq, rec, p->w1, Cin, p->b1, t.stat1, p->w2, p->b2, t.stat2, ew,
                                  nullptr, nullptr, nullptr, base, ldbase, out, ldo, st));
           } else {
             YOLAT_TRY(edge_agg(g, N, C, t.z2, t.stat2, ew, base, ldbase, out, ldo, st));
@@ -166,7 +171,7 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
         } else {
           YOLAT_TRY(bn_finalize_from_partials(nullptr, 0, E, C, &p->bn2, 0, t.stat2, st));
           if (br) join_branch(br, 1, st);
-          YOLAT_TRY(edge_fused(g, N, E, EF_AGG | (no_tape ? 0 : EF_TAPE), pq, ldpq, attr, p->w1, Cin, p->b1, t.stat1,
+          YOLAT_TRY(edge_fused(g, N, E, EF_AGG | (no_tape ? 0 : EF_TAPE), pq, ldpq, rec, p->w1, Cin, p->b1, t.stat1,
                                p->w2, p->b2, t.stat2, ew, t.z1, t.z2, nullptr, base, ldbase, out, ldo, st));
         }
       }
@@ -210,7 +215,7 @@ static int gp2_bwd_impl(const yolat_gp2_params* p, const yolat_gp2_grads* gr, in
   GraphView g;
   if (!dry) graph_layout(N, E, graph, &g);
   int acc_dx = accumulate_dx, acc_dxn = accumulate_dx;
-  Branches* br = dry ? nullptr : branches();
+  Branches* br = (dry || N > kBranchMaxNodes) ? nullptr : branches();
   cudaStream_t st_node = br ? br->side[0] : st, st_linr = br ? br->side[1] : st;
   if (br) fork_branches(br, st);
 

@@ -3,28 +3,34 @@
 // Reference chain (gcn_lib/sparse/torch_vertex.py:324-337 + PyG propagate + torch_nn.py:58-68 + scatter-mean):
 //     x_i, x_j = index_select ; f = cat(x_i, x_j - x_i, attr) ; z1 = Lin1(f) ; a1 = relu(bn1(z1)) ;
 //     z2 = Lin2(a1) ; m = relu(bn2(z2)) ; out[i] = mean_{e -> i} m_e
-// which materialises eight [E, *] tensors.  Here one persistent CTA per SM (512 threads, 128 registers each, ~220 KB
+// which materialises eight [E, *] tensors.  Here one persistent CTA per SM (512 or 640 threads, ~220 KB
 // of shared memory) owns a contiguous range of target rows (CSR slots are sorted by target) and streams it in tiles
 // of 128 slots through mbarrier-connected warp roles -- no CTA-wide barrier inside the loop:
-//   ring fill   (epilogue warps, ahead of their own work): dst / src byte offsets and the attribute row of every slot
-//               of the next tiles -> 8-stage shared-memory ring (3-step register pipeline over the eid -> attr chain);
-//   gather      (8 warps): P[dst] + Q[src] + W1c attr + b1 (Lin1 pre-reduced to node level: P = x (W1a-W1b)^T,
-//               Q = x W1b^T), BN1 + ReLU in registers, 3xTF32 hi/lo split written straight into the SWIZZLE_128B
-//               K-major a1 stage of the tensor core (2 stages); the P / Q rows of tile t+1 are requested slot by slot
-//               while tile t is computed (8 slots x 2 rows per thread always in flight); a1 never exists in HBM;
-//   MMA         (one elected lane of gather warp t % 8, polling a_full between slots): 24 tcgen05.mma.kind::tf32
-//               (128 x 64 x 8; W2 hi/lo resident in shared memory, BN2 scale folded into its rows for F_AGG),
-//               z2 accumulates in TMEM (2 x 64 columns);
-//   epilogue    (8 warps, tcgen05.ld 32 lanes x 32 columns each):
-//        F_STATS: BatchNorm-2 batch statistics in registers (training needs them before any output exists),
-//        F_AGG:   BN2 + ReLU (+ edge weight) -> staging tile -> segmented mean per target row (4 threads x 16
-//                 channels per row, rows finishing in the tile are written once as base + mean, the straddling row
-//                 goes through a carry) -- no atomics, fixed summation order, no read-modify-write of `out`,
+//   gather      (16 warps; thread = 4 channels x 4 slots of every tile): P[dst] + Q[src] + W1c attr + b1 (Lin1
+//               pre-reduced to node level: P = x (W1a-W1b)^T, Q = x W1b^T), BN1 + ReLU in packed fp32 pairs
+//               (FFMA2 / FADD2), truncating 3xTF32 hi/lo split written straight into the SWIZZLE_128B K-major a1
+//               stage of the tensor core (2 stages); the P / Q rows of tile t+1 are requested slot by slot while
+//               tile t is computed (4 slots x 2 rows per thread always in flight = 64 KB per SM); straight-line code
+//               with no polling inside, so the compiler interleaves the four slots; a1 never exists in HBM;
+//   ring        slot-ordered records (k_edge_records, once per layer call: P / Q byte offsets | attribute row, 16 B each)
+//               reach a 6-stage shared-memory ring as two TMA bulk copies per tile (cp.async.bulk + mbarrier
+//               complete_tx), issued by one elected lane five tiles ahead -- no thread touches an index on the way;
+//   epilogue    (4 or 8 warps, thread = one slot = one TMEM lane):
+//        MMA:   warp 0 waits for the a1 stage of tile t and issues 24 tcgen05.mma.kind::tf32 (128 x 64 x 8; W2 hi/lo
+//               resident in shared memory, BN2 scale folded into its rows for F_AGG) before it drains tile t-1, so
+//               the product of tile t overlaps the epilogue of t-1 and the gathers of t+1; z2 accumulates in TMEM
+//               (2 x 64 columns);
+//        drain: tcgen05.ld (32 lanes x 32 columns, twice) -> staging tile [slot][channel] in shared memory, then
+//        F_STATS: BatchNorm-2 batch statistics as column sums of the staging tile (training needs them before any
+//                 output exists),
+//        F_AGG:   BN2 + ReLU (+ edge weight) -> segmented mean per target row (4 threads x 16 channels per row, rows
+//                 finishing in the tile are written once as base + mean, the straddling row goes through a carry)
+//                 -- no atomics, fixed summation order, no read-modify-write of `out`,
 //        F_TAPE:  z1 / z2 for the backward pass (only when autograd needs them),
 //        F_Z1:    pass A -- only the gather half runs and accumulates the BatchNorm-1 statistics of z1.
 // Training forward = F_Z1 + F_STATS + F_AGG launches; nothing of size [E, C] touches HBM unless F_TAPE is set.
-// Measured bound (profiles/): the SM <-> L2 path of the row gathers plus the shared-memory bandwidth of the 3xTF32
-// operand reads (A and B are each read three times per k-step); see DESIGN.md section 3.
+// Measured bound (profiles/): issue slots of the gather warps and the SM <-> L1/L2 path of the row gathers; see
+// DESIGN.md section 3.
 #include <cstdlib>
 #include "common.cuh"
 #include "tc.cuh"
@@ -36,20 +42,19 @@ using namespace tc;
 
 constexpr int C = 64;             // channels (n_filters of the README configs)
 constexpr int TILE = 128;         // CSR slots per MMA tile = TMEM lanes
-constexpr int E_WARPS = 8;        // warps 0..7: epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2);
-                                  // warps 4..7 also fill the index ring, lane 0 of warp 0 issues the tcgen05.mma
-constexpr int G_WARPS = 8;        // warps 8..15: gather + Lin1 + BN1 + ReLU + 3xTF32 split
-constexpr int E_THREADS = E_WARPS * 32, G_THREADS = G_WARPS * 32;
-constexpr int THREADS = E_THREADS + G_THREADS;          // 512 threads x 128 registers = the whole register file
+// Warp roles are template parameters <EW, GW>: EW epilogue warps (4: one thread per slot draining both column halves;
+// 8: TMEM lane quarter = warp & 3, column half = warp >> 2) and GW gather warps (16 threads per slot, 64 / GW slots per
+// thread and tile).  Warps 0..3 also fill the index ring, warp 0 issues the MMAs.
 constexpr uint32_t A_KB = TILE * 128;      // one k-block (32 channels) of the a1 tile: 16 KB
 constexpr uint32_t A_HI = 2 * A_KB;        // hi part (2 k-blocks): 32 KB; lo follows
 constexpr uint32_t A_STAGE = 2 * A_HI;     // one a1 stage: 64 KB; two stages
 constexpr uint32_t W_KB = C * 128;         // one k-block of W2: 8 KB
 constexpr uint32_t W_HI = 2 * W_KB;        // 16 KB; lo follows
-constexpr int LDS = C + 4;                 // padded row of the message staging tile
-constexpr int RING = 8;                    // index ring stages (tiles)
-constexpr int PF = 4;                      // ring steps (of two tiles) the fill runs ahead of the epilogue
-constexpr int RING_BYTES = TILE * 8 + TILE * 16;          // per stage: (dst, src) int2 per slot | attr float4 per slot
+constexpr int LDS = C + 4;                 // padded row of the staging tile
+constexpr int RING = 6;                    // record ring stages (tiles)
+constexpr int PF = RING - 1;               // tiles the TMA producer runs ahead of the tile being drained
+constexpr int PFL2 = 3;                    // tiles the L2 prefetch of the P / Q rows runs ahead of the gather
+constexpr int RING_BYTES = TILE * 16 + TILE * 16;         // per stage: (P off, Q off, eid, 0) int4 per slot | attr float4 per slot
 constexpr uint32_t OFF_W = 2 * A_STAGE;
 constexpr uint32_t OFF_STAGE = OFF_W + 2 * W_HI;
 constexpr uint32_t OFF_RING = OFF_STAGE + TILE * LDS * 4;
@@ -57,7 +62,6 @@ constexpr uint32_t OFF_CARRY = OFF_RING + RING * RING_BYTES;
 constexpr uint32_t OFF_BN2 = OFF_CARRY + 2 * C * 4;
 constexpr uint32_t SMEM_BYTES = OFF_BN2 + 2 * C * 4 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(2 * TILE * (C + 1) * 4 <= 2 * A_STAGE, "final statistics reduction aliases the a1 ring");
 
 enum { F_TAPE = 1, F_STATS = 2, F_AGG = 4, F_Z1 = 8 };   // F_Z1: pass A -- BatchNorm-1 statistics of z1 only (no MMA)
 
@@ -65,7 +69,8 @@ struct Params {
   const int32_t* rowptr; const int32_t* src; const int32_t* dst; const int32_t* eid; const float* deg_inv;
   int64_t N, E;
   const float* pq; uint32_t ldpq;  // [N, ldpq]: P at column 0, Q at column C (N * ldpq < 2^30)
-  const float* attr;          // [E, 4] original edge order
+  const int4* rec_idx;        // [E] slot order: (byte offset of P[dst], byte offset of Q[src] relative to P, eid, 0)
+  const float4* rec_attr;     // [E] slot order: attribute row of the slot's edge
   const float* w1c; int ld1;  // W1[:, 2Cin:2Cin+4], row stride ld1
   const float* b1;            // [C] or null
   const float* stat1;         // BN1 (sc | sh)
@@ -74,7 +79,7 @@ struct Params {
   const float* stat2;         // BN2 (sc | sh), F_AGG only
   const float* ew;            // [E] or null
   float* z1; float* z2;       // tape [E, C] in slot order, F_TAPE only
-  float* part;                // [gridDim.x][2][C], F_STATS only
+  float* part;                // [gridDim.x][2][C], F_STATS / F_Z1
   const float* base; int64_t ldb;   // [N, C] added to the mean (lin_r(x)); may alias out; F_AGG only
   float* out; int64_t ldo;    // [N, C] = base + mean, F_AGG only: every row of the CTA's range is written once
 };
@@ -87,12 +92,29 @@ __device__ __forceinline__ int row_at_or_after(const Params& p, int64_t s) {
   return (p.rowptr[v] == (int32_t)s) ? v : v + 1;
 }
 
+// one arrival per warp: every lane's earlier shared-memory accesses are ordered before it by the warp barrier
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
 // Persistent, warp-specialised: one CTA per SM owns a contiguous, row-aligned range of CSR slots and walks it in
 // tiles of 128 slots through a pipeline of mbarrier-connected roles (no CTA-wide barrier inside the loop):
-//     ring fill (idx, attr; 3 tiles ahead)  ->  gather warps  --a1 stage (smem, UMMA layout, 2 stages)-->
+//     ring fill (idx, attr; PF - 4 tiles ahead)  ->  gather warps  --a1 stage (smem, UMMA layout, 2 stages)-->
 //     tcgen05.mma  --z2 accumulator (TMEM, 2 x 64 columns)-->  epilogue warps (statistics | segmented mean | tape)
-template <int FLAGS>
-__global__ void __launch_bounds__(THREADS, 1) k_edge_fused(const Params p) {
+template <int FLAGS, int E_WARPS, int G_WARPS, bool MMA_G>
+__global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(const Params p) {
+  constexpr int E_THREADS = E_WARPS * 32, G_THREADS = G_WARPS * 32, THREADS = E_THREADS + G_THREADS;
+  constexpr int SPT = TILE * 16 / G_THREADS;              // slots per gather thread and tile (16 threads per slot)
+  constexpr int NSLG = TILE / SPT;                        // slot groups: slot = i * NSLG + sl
+  constexpr int NSG = E_THREADS / 16;                     // F_STATS: slot groups of the column sums
+  constexpr int TPR = 4;                                  // F_AGG: threads per target row
+  constexpr int RIF = E_THREADS / TPR;                    // F_AGG: rows in flight (their bookkeeping is prefetched)
+  constexpr int CPT = 16 / TPR;                           // F_AGG: 16-byte chunks per thread (chunk k at ch + 4 TPR k)
+  static_assert(E_WARPS == 4 || E_WARPS == 8, "epilogue mapping");
+  static_assert(SPT * G_THREADS == TILE * 16 && (SPT == 4 || SPT == 8), "gather mapping");
+  static_assert(2 * (G_THREADS / 16) * C * 4 <= 2 * A_STAGE, "pass A reduction aliases the a1 ring");
+  static_assert(2 * NSG * C * 4 <= TILE * LDS * 4, "statistics reduction aliases the staging tile");
   constexpr bool FOLD = (FLAGS & F_AGG) && !(FLAGS & F_TAPE);   // the tape needs the unscaled z2
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_a_full[2], bar_a_empty[2], bar_acc_full[2], bar_acc_empty[2];
@@ -114,19 +136,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_fused(const Params p) {
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bar_a_full[i]), G_THREADS);
+      mbar_init(smem_u32(&bar_a_full[i]), G_WARPS);
       mbar_init(smem_u32(&bar_a_empty[i]), 1);
       mbar_init(smem_u32(&bar_acc_full[i]), 1);
       mbar_init(smem_u32(&bar_acc_empty[i]), E_THREADS);
     }
 #pragma unroll
     for (int i = 0; i < RING; ++i) {
-      mbar_init(smem_u32(&bar_ring_full[i]), TILE);
-      mbar_init(smem_u32(&bar_ring_empty[i]), G_THREADS);
+      mbar_init(smem_u32(&bar_ring_full[i]), 1);
+      mbar_init(smem_u32(&bar_ring_empty[i]), G_WARPS);
     }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 2 * C);
+
+  // The slots of a partial last tile keep whatever the stage held before: zeros (node 0) until the ring has wrapped.
+  for (int idx = tid; idx < RING * RING_BYTES / 16; idx += THREADS)
+    reinterpret_cast<int4*>(ring)[idx] = make_int4(0, 0, 0, 0);
 
   // W2 (B operand, K-major: row n = output channel, 64 k) -> hi/lo, resident for the whole kernel
   if (!(FLAGS & F_Z1))
@@ -146,7 +172,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_fused(const Params p) {
     bn2_s[tid] = sc;
     bn2_s[C + tid] = fmaf(p.b2 ? __ldg(p.b2 + tid) : 0.f, sc, sh);
   }
-  fence_proxy_async_smem();
+  fence_proxy_async_smem();                        // generic-proxy writes (ring zeros, W2) before async-proxy accesses
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -159,109 +185,93 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_fused(const Params p) {
   const int64_t s_end = r_end < p.N ? p.rowptr[r_end] : p.E;
   const int ntiles = (int)((s_end - s_begin + TILE - 1) / TILE);
 
-  // ---- tcgen05.mma issue: z2 = a1 W2^T, 3xTF32, accumulator (tile & 1) in TMEM.  Called by a whole (converged) warp
-  //      once a_full[t & 1] has completed; one elected lane issues.  The duty rotates over the gather warps: warp t % 8
-  //      polls a_full (non-blocking) between the slots of tile t+1, so the product of tile t starts as soon as its
-  //      last gather warp has arrived and overlaps both the gathers of tile t+1 and the epilogue of tile t-1.
+  // ---- tcgen05.mma issue: z2 = a1 W2^T, 3xTF32, accumulator (tile & 1) in TMEM.  Called by one whole warp, one
+  //      elected lane issues.  MMA_G: gather warp t % G_WARPS, after its own arrival, waits for the other gather warps
+  //      (they finish within a few hundred cycles of each other), so the product of tile t starts the moment its a1
+  //      stage is complete; the duty rotates over the warps.  !MMA_G: epilogue warp 0, one tile ahead of its drain.
+  //      Either way the product of tile t overlaps the epilogue of tile t-1 and the gathers of tile t+1.
   auto issue_mma = [&](int t) {
     constexpr uint32_t IDESC = make_idesc(TILE, C, 0, 0);
     const int s = t & 1;
     const uint32_t a_u32 = sm_u32 + (uint32_t)s * A_STAGE, w_u32 = sm_u32 + OFF_W;
-    if (t >= 2) mbar_wait(smem_u32(&bar_acc_empty[s]), (uint32_t)(((t >> 1) - 1) & 1));
+    mbar_wait_park(smem_u32(&bar_a_full[s]), (uint32_t)((t >> 1) & 1));
+    if (t >= 2) mbar_wait_park(smem_u32(&bar_acc_empty[s]), (uint32_t)(((t >> 1) - 1) & 1));
     tc_fence_after();
     const uint32_t d = tmem_d + (uint32_t)(s * C);
     if (elect_one_sync()) {
 #pragma unroll
-    for (int kb = 0; kb < 2; ++kb) {
+      for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t ao = (uint32_t)kb * A_KB + (uint32_t)ks * 32u;
-        const uint32_t bo = (uint32_t)kb * W_KB + (uint32_t)ks * 32u;
-        const uint64_t a_hi = make_desc(a_u32 + ao, 16, 1024, LAYOUT_SW128);
-        const uint64_t a_lo = make_desc(a_u32 + A_HI + ao, 16, 1024, LAYOUT_SW128);
-        const uint64_t b_hi = make_desc(w_u32 + bo, 16, 1024, LAYOUT_SW128);
-        const uint64_t b_lo = make_desc(w_u32 + W_HI + bo, 16, 1024, LAYOUT_SW128);
-        umma_tf32(d, a_lo, b_hi, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
-        umma_tf32(d, a_hi, b_lo, IDESC, 1u);
-        umma_tf32(d, a_hi, b_hi, IDESC, 1u);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t ao = (uint32_t)kb * A_KB + (uint32_t)ks * 32u;
+          const uint32_t bo = (uint32_t)kb * W_KB + (uint32_t)ks * 32u;
+          const uint64_t a_hi = make_desc(a_u32 + ao, 16, 1024, LAYOUT_SW128);
+          const uint64_t a_lo = make_desc(a_u32 + A_HI + ao, 16, 1024, LAYOUT_SW128);
+          const uint64_t b_hi = make_desc(w_u32 + bo, 16, 1024, LAYOUT_SW128);
+          const uint64_t b_lo = make_desc(w_u32 + W_HI + bo, 16, 1024, LAYOUT_SW128);
+          umma_tf32(d, a_lo, b_hi, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
+          umma_tf32(d, a_hi, b_lo, IDESC, 1u);
+          umma_tf32(d, a_hi, b_hi, IDESC, 1u);
+        }
       }
-    }
-    umma_commit(smem_u32(&bar_acc_full[s]));    // z2 of this tile is complete ...
-    umma_commit(smem_u32(&bar_a_empty[s]));     // ... and its a1 stage may be refilled
+      umma_commit(smem_u32(&bar_acc_full[s]));    // z2 of this tile is complete ...
+      umma_commit(smem_u32(&bar_a_empty[s]));     // ... and its a1 stage may be refilled
     }
     __syncwarp();
   };
 
   if (warp < E_WARPS) {
     // =========================== epilogue warps ==========================================================
-    const int q = warp & 3, h = warp >> 2, slot = q * 32 + lane, et = tid;
+    const int q = warp & 3, slot = q * 32 + lane, et = tid;
+    const int h_begin = E_WARPS == 8 ? (warp >> 2) : 0, h_end = E_WARPS == 8 ? h_begin + 1 : 2;
 
-    // ---- index ring fill (one slot per thread; warps 0..3 serve the even tiles, warps 4..7 the odd ones), a 3-step
-    //      register pipeline so that neither of the two dependent global loads (edge id -> attribute row) is waited for.
-    //      With T(j) = 2j + h:  step j: store tile T(j-2) | load attr of T(j-1) (its eid arrived during the previous
-    //      step) | load idx of T(j)
-    const uint32_t ldpq_b = p.ldpq * 4u;             // the ring carries byte offsets of the P / Q rows
-    int2 ds0 = make_int2(0, 0), ds1 = make_int2(0, 0);
-    int e1 = 0;
-    float4 at0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto ring_step = [&](int j) {
-      // (a) store tile T(j - 2)
-      const int ts = 2 * (j - 2) + h;
-      if (ts >= 0 && ts < ntiles) {
-        const int st = ts & (RING - 1);
-        if (ts >= RING) mbar_wait(smem_u32(&bar_ring_empty[st]), (uint32_t)(((ts / RING) - 1) & 1));
-        uint8_t* rg = ring + st * RING_BYTES;
-        reinterpret_cast<int2*>(rg)[slot] = ds0;
-        reinterpret_cast<float4*>(rg + TILE * 8)[slot] = at0;
-        mbar_arrive(smem_u32(&bar_ring_full[st]));
-      }
-      // (b) attribute row of tile T(j - 1)
-      ds0 = ds1;
-      at0 = make_float4(0.f, 0.f, 0.f, 0.f);
-      {
-        const int64_t s = s_begin + (int64_t)(2 * (j - 1) + h) * TILE + slot;
-        if (j >= 1 && s < s_end) at0 = __ldg(reinterpret_cast<const float4*>(p.attr + (int64_t)e1 * 4));
-      }
-      // (c) indices of tile T(j) (padding slots read node 0 / edge 0 and are masked downstream)
-      {
-        const int64_t s = s_begin + (int64_t)(2 * j + h) * TILE + slot;
-        ds1 = make_int2(0, 0);
-        e1 = 0;
-        if (s < s_end) {
-          ds1 = make_int2((int)((uint32_t)__ldg(p.dst + s) * ldpq_b), (int)((uint32_t)__ldg(p.src + s) * ldpq_b));
-          e1 = __ldg(p.eid + s);
-        }
-      }
+    // ---- record ring producer (thread 0): two TMA bulk copies per tile, completion counted in bytes on
+    //      ring_full[stage]; a stage is refilled once every gather warp has released it.
+    auto fill = [&](int j) {
+      if (j >= ntiles) return;
+      const int st = j % RING;
+      if (j >= RING) mbar_wait_park(smem_u32(&bar_ring_empty[st]), (uint32_t)(((j / RING) - 1) & 1));
+      const int64_t s0 = s_begin + (int64_t)j * TILE;
+      const uint32_t bytes = (uint32_t)min((int64_t)TILE, s_end - s0) * 16u;
+      const uint32_t bar = smem_u32(&bar_ring_full[st]);
+      const uint32_t dst = smem_u32(ring + st * RING_BYTES);
+      mbar_expect_tx(bar, 2u * bytes);
+      bulk_g2s(dst, p.rec_idx + s0, bytes, bar);
+      bulk_g2s(dst + TILE * 16, p.rec_attr + s0, bytes, bar);
     };
-    for (int j = 0; j < PF; ++j) ring_step(j);       // tiles 0 .. 2 PF - 5 are in the ring, two more pairs in flight
-
-    if (FLAGS & F_Z1) {                              // pass A: no accumulator to drain, only keep the ring filled
-      for (int j = PF; 2 * (j - 2) + h < ntiles; ++j) ring_step(j);
-    } else {
-    float st_s[32], st_ss[32];
-    if (FLAGS & F_STATS) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) { st_s[i] = 0.f; st_ss[i] = 0.f; }
+    const bool producer = (tid == 0);
+    if (producer) {
+      for (int j = 0; j < PF; ++j) fill(j);
     }
-    // F_AGG: row bookkeeping of the next tile is fetched one tile ahead
-    const int ch = (et & 3) * 4;                     // 4 threads per row, channels ch + 16k (k = 0..3): 64 rows in flight,
-                                                     // 64-byte contiguous per k across the 4 threads (no bank conflicts)
+    if (FLAGS & F_Z1) {                              // pass A: no accumulator to drain, only keep the ring filled
+      if (producer) {
+        for (int j = PF; j < ntiles; ++j) fill(j);
+      }
+    } else {
+    float2 st_s[2], st_ss[2];                        // F_STATS: channels 4 cg .. 4 cg + 3 of TILE / NSG slots
+    st_s[0] = st_s[1] = st_ss[0] = st_ss[1] = make_float2(0.f, 0.f);
+    const int cg = et & 15, sp = et >> 4;
+    // F_AGG: TPR threads per row, this thread's chunks are channels ch + 4 TPR k (k < CPT): 16 TPR contiguous bytes per
+    // k across the threads of a row (no bank conflicts); row bookkeeping of the next tile is fetched one tile ahead
+    const int ch = (et % TPR) * 4;
+    const int rl = et / TPR;                         // row lane: 0 .. RIF - 1
     int R_prev = r_begin;
     int R_cur = 0;
     int nb = 0, ne_ = 0;                             // rowptr[r], rowptr[r + 1] of this thread's first row of the tile
     float ndi = 0.f;
-    float4 nbase[4];
-    auto row_meta = [&](int r, int& b, int& e, float& di, float4 (&bs)[4], bool want) {
+    float4 nbase[CPT];
+    auto row_meta = [&](int r, int& b, int& e, float& di, float4 (&bs)[CPT], bool want) {
       b = 0; e = 0; di = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) bs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < CPT; ++k) bs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (want && r < p.N) {
         b = __ldg(p.rowptr + r);
         e = __ldg(p.rowptr + r + 1);
         di = __ldg(p.deg_inv + r);
         if (p.base) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) bs[k] = __ldg(reinterpret_cast<const float4*>(p.base + (int64_t)r * p.ldb + ch + 16 * k));
+          for (int k = 0; k < CPT; ++k)
+            bs[k] = __ldg(reinterpret_cast<const float4*>(p.base + (int64_t)r * p.ldb + ch + 4 * TPR * k));
         }
       }
     };
@@ -271,105 +281,134 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_fused(const Params p) {
     };
     if ((FLAGS & F_AGG) && ntiles > 0) {
       R_cur = tile_rcur(0);
-      row_meta(R_prev + (et >> 2), nb, ne_, ndi, nbase, true);
+      row_meta(R_prev + rl, nb, ne_, ndi, nbase, true);
     }
 
-    for (int it = 0; it < ntiles; ++it) {
-      const int a = it & 1;
-      const int64_t s0 = s_begin + (int64_t)it * TILE;
+    if (!MMA_G && warp == 0 && ntiles > 0) issue_mma(0);
+    for (int t = 0; t < ntiles; ++t) {
+      if (producer) fill(t + PF);                    // never blocks in practice: the gather finished tile t - 1 long ago
+      if (!MMA_G && warp == 0 && t + 1 < ntiles) issue_mma(t + 1);
+      const int a = t & 1;
+      const int64_t s0 = s_begin + (int64_t)t * TILE;
       const int nvalid = (int)min((int64_t)TILE, s_end - s0);
-      if ((it & 1) == h) ring_step((it >> 1) + PF);   // stores tile it + 2 PF - 4
-      mbar_wait_sleep(smem_u32(&bar_acc_full[a]), (uint32_t)((it >> 1) & 1));
+      float wgt = 1.f;
+      if ((FLAGS & F_AGG) && p.ew && slot < nvalid) wgt = __ldg(p.ew + __ldg(p.eid + s0 + slot));
+      mbar_wait_park(smem_u32(&bar_acc_full[a]), (uint32_t)((t >> 1) & 1));
       tc_fence_after();
-      float v[32];
-      tmem_ld32(tmem_d + (uint32_t)(a * C) + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32), v);
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bar_acc_empty[a]));     // the accumulator is free for tile it + 2
-
-      if (FLAGS & F_TAPE) {
-        if (slot < nvalid) {
-          float* d = p.z2 + (s0 + slot) * C + h * 32;
+      named_bar_sync(1, E_THREADS);                 // the readers of the previous tile's staging rows have finished
+      for (int h = h_begin; h < h_end; ++h) {
+        float v[32];
+        tmem_ld32(tmem_d + (uint32_t)(a * C) + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32), v);
+        if (h == h_end - 1) {
+          tc_fence_before();
+          mbar_arrive(smem_u32(&bar_acc_empty[a]));   // the accumulator is free for tile t + 2
+        }
+        if (FLAGS & F_TAPE) {
+          if (slot < nvalid) {
+            float* d = p.z2 + (s0 + slot) * C + h * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.b2) b = __ldg(reinterpret_cast<const float4*>(p.b2 + h * 32 + i));
+              *reinterpret_cast<float4*>(d + i) = make_float4(v[i] + b.x, v[i + 1] + b.y, v[i + 2] + b.z, v[i + 3] + b.w);
+            }
+          }
+        }
+        float* d = stage + slot * LDS + h * 32;
+        if (FLAGS & F_STATS) {
+          // raw accumulator values of the valid slots (zeros elsewhere); the bias enters analytically at the end
+          const float m = slot < nvalid ? 1.f : 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(d + i) = make_float4(v[i] * m, v[i + 1] * m, v[i + 2] * m, v[i + 3] * m);
+        }
+        if (FLAGS & F_AGG) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.b2) b = __ldg(reinterpret_cast<const float4*>(p.b2 + h * 32 + i));
-            *reinterpret_cast<float4*>(d + i) = make_float4(v[i] + b.x, v[i + 1] + b.y, v[i + 2] + b.z, v[i + 3] + b.w);
+            const float4 sh = *reinterpret_cast<const float4*>(bn2_s + C + h * 32 + i);
+            float4 m;
+            if (FOLD) {
+              m.x = fmaxf(v[i] + sh.x, 0.f);
+              m.y = fmaxf(v[i + 1] + sh.y, 0.f);
+              m.z = fmaxf(v[i + 2] + sh.z, 0.f);
+              m.w = fmaxf(v[i + 3] + sh.w, 0.f);
+            } else {
+              const float4 sc = *reinterpret_cast<const float4*>(bn2_s + h * 32 + i);
+              m.x = fmaxf(fmaf(v[i], sc.x, sh.x), 0.f);
+              m.y = fmaxf(fmaf(v[i + 1], sc.y, sh.y), 0.f);
+              m.z = fmaxf(fmaf(v[i + 2], sc.z, sh.z), 0.f);
+              m.w = fmaxf(fmaf(v[i + 3], sc.w, sh.w), 0.f);
+            }
+            if (p.ew) { m.x *= wgt; m.y *= wgt; m.z *= wgt; m.w *= wgt; }
+            *reinterpret_cast<float4*>(d + i) = m;
           }
         }
       }
+      named_bar_sync(1, E_THREADS);
       if (FLAGS & F_STATS) {
-        // raw accumulator sums over the valid slots; the bias enters analytically at the end
-        if (slot < nvalid) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { st_s[i] += v[i]; st_ss[i] = fmaf(v[i], v[i], st_ss[i]); }
+        // column sums of the staging tile: this thread owns 4 channels of TILE / NSG slots
+#pragma unroll 4
+        for (int j = 0; j < TILE / NSG; ++j) {
+          const float4 m = *reinterpret_cast<const float4*>(stage + (sp * (TILE / NSG) + j) * LDS + cg * 4);
+          const float2 m0 = make_float2(m.x, m.y), m1 = make_float2(m.z, m.w);
+          st_s[0] = fadd2(st_s[0], m0);
+          st_s[1] = fadd2(st_s[1], m1);
+          st_ss[0] = ffma2(m0, m0, st_ss[0]);
+          st_ss[1] = ffma2(m1, m1, st_ss[1]);
         }
       }
       if (FLAGS & F_AGG) {
-        float wgt = 1.f;
-        if (p.ew && slot < nvalid) wgt = __ldg(p.ew + __ldg(p.eid + s0 + slot));
-        named_bar_sync(1, E_THREADS);               // the row loop of the previous tile has finished reading `stage`
-        float* d = stage + slot * LDS + h * 32;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 sh = *reinterpret_cast<const float4*>(bn2_s + C + h * 32 + i);
-          float4 m;
-          if (FOLD) {
-            m.x = fmaxf(v[i] + sh.x, 0.f);
-            m.y = fmaxf(v[i + 1] + sh.y, 0.f);
-            m.z = fmaxf(v[i + 2] + sh.z, 0.f);
-            m.w = fmaxf(v[i + 3] + sh.w, 0.f);
-          } else {
-            const float4 sc = *reinterpret_cast<const float4*>(bn2_s + h * 32 + i);
-            m.x = fmaxf(fmaf(v[i], sc.x, sh.x), 0.f);
-            m.y = fmaxf(fmaf(v[i + 1], sc.y, sh.y), 0.f);
-            m.z = fmaxf(fmaf(v[i + 2], sc.z, sh.z), 0.f);
-            m.w = fmaxf(fmaf(v[i + 3], sc.w, sh.w), 0.f);
-          }
-          if (p.ew) { m.x *= wgt; m.y *= wgt; m.z *= wgt; m.w *= wgt; }
-          *reinterpret_cast<float4*>(d + i) = m;
-        }
-        named_bar_sync(1, E_THREADS);
         // Segmented mean by target row.  This tile finishes rows [R_prev, R_cur); row R_cur (if it has slots here)
-        // continues in the next tile and goes to the carry.  4 threads (16 channels each) per row, 64 rows in flight;
-        // the bookkeeping of each thread's first row was loaded during the previous tile.
+        // continues in the next tile and goes to the carry.  TPR threads per row, RIF rows in flight; the bookkeeping of
+        // each thread's first row was loaded during the previous tile.
         const int64_t s1 = s0 + nvalid;
         const bool last = s1 >= s_end;
-        const float* cin = carry + (it & 1) * C;
-        float* cout = carry + ((it + 1) & 1) * C;
+        const float* cin = carry + (t & 1) * C;
+        float* cout = carry + ((t + 1) & 1) * C;
         int b = nb, e = ne_;
         float di = ndi;
-        float4 bs[4] = {nbase[0], nbase[1], nbase[2], nbase[3]};
-        const int R_next = (it + 1 < ntiles) ? tile_rcur(it + 1) : r_end;     // used one tile later
-        row_meta(R_cur + (et >> 2), nb, ne_, ndi, nbase, it + 1 < ntiles);    // first row of the next tile
-        for (int r = R_prev + (et >> 2); r <= R_cur; r += E_THREADS / 4) {
+        float4 bs[CPT];
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) bs[k] = nbase[k];
+        const int R_next = (t + 1 < ntiles) ? tile_rcur(t + 1) : r_end;      // used one tile later
+        row_meta(R_cur + rl, nb, ne_, ndi, nbase, t + 1 < ntiles);           // first row of the next tile
+        for (int r = R_prev + rl; r <= R_cur; r += RIF) {
           if (r == R_cur && last) break;
-          if (r != R_prev + (et >> 2)) row_meta(r, b, e, di, bs, true);
+          if (r != R_prev + rl) row_meta(r, b, e, di, bs, true);
           const bool done = r < R_cur;
           if (!done && (int64_t)b >= s1) break;     // the next row starts exactly at the tile boundary: nothing to carry
-          float4 acc[4];
+          float2 acc[2 * CPT];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = 0; k < 2 * CPT; ++k) acc[k] = make_float2(0.f, 0.f);
           if ((int64_t)b < s0) {                    // the row started in an earlier tile
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc[k] = *reinterpret_cast<const float4*>(cin + ch + 16 * k);
+            for (int k = 0; k < CPT; ++k) {
+              const float4 m = *reinterpret_cast<const float4*>(cin + ch + 4 * TPR * k);
+              acc[2 * k] = make_float2(m.x, m.y);
+              acc[2 * k + 1] = make_float2(m.z, m.w);
+            }
           }
           const int lo = (int)(max((int64_t)b, s0) - s0), hi = (int)(min((int64_t)e, s1) - s0);
           for (int j = lo; j < hi; ++j) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float4 m = *reinterpret_cast<const float4*>(stage + j * LDS + ch + 16 * k);
-              acc[k].x += m.x; acc[k].y += m.y; acc[k].z += m.z; acc[k].w += m.w;
+            for (int k = 0; k < CPT; ++k) {
+              const float4 m = *reinterpret_cast<const float4*>(stage + j * LDS + ch + 4 * TPR * k);
+              acc[2 * k] = fadd2(acc[2 * k], make_float2(m.x, m.y));
+              acc[2 * k + 1] = fadd2(acc[2 * k + 1], make_float2(m.z, m.w));
             }
           }
           if (done) {
             float* o = p.out + (int64_t)r * p.ldo + ch;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              *reinterpret_cast<float4*>(o + 16 * k) = make_float4(fmaf(acc[k].x, di, bs[k].x), fmaf(acc[k].y, di, bs[k].y),
-                                                                  fmaf(acc[k].z, di, bs[k].z), fmaf(acc[k].w, di, bs[k].w));
+            for (int k = 0; k < CPT; ++k)
+              *reinterpret_cast<float4*>(o + 4 * TPR * k) =
+                  make_float4(fmaf(acc[2 * k].x, di, bs[k].x), fmaf(acc[2 * k].y, di, bs[k].y),
+                              fmaf(acc[2 * k + 1].x, di, bs[k].z), fmaf(acc[2 * k + 1].y, di, bs[k].w));
           } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(cout + ch + 16 * k) = acc[k];
+            for (int k = 0; k < CPT; ++k)
+              *reinterpret_cast<float4*>(cout + ch + 4 * TPR * k) =
+                  make_float4(acc[2 * k].x, acc[2 * k].y, acc[2 * k + 1].x, acc[2 * k + 1].y);
           }
         }
         R_prev = R_cur;
@@ -377,30 +416,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_fused(const Params p) {
       }
     }
     if ((FLAGS & F_AGG) && ntiles == 0) {           // a range of rows without a single slot: out = base
-      for (int r = r_begin + (et >> 2); r < r_end; r += E_THREADS / 4) {
+      for (int r = r_begin + rl; r < r_end; r += RIF) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < CPT; ++k) {
           float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.base) b0 = __ldg(reinterpret_cast<const float4*>(p.base + (int64_t)r * p.ldb + ch + 16 * k));
-          *reinterpret_cast<float4*>(p.out + (int64_t)r * p.ldo + ch + 16 * k) = b0;
+          if (p.base) b0 = __ldg(reinterpret_cast<const float4*>(p.base + (int64_t)r * p.ldb + ch + 4 * TPR * k));
+          *reinterpret_cast<float4*>(p.out + (int64_t)r * p.ldo + ch + 4 * TPR * k) = b0;
         }
       }
     }
     if (FLAGS & F_STATS) {
-      // every MMA of this CTA has completed (the last accumulator was read above): the a1 ring is free
-      float* S = reinterpret_cast<float*>(sm);
-      float* SS = S + TILE * (C + 1);
+      // combine the NSG slot groups through the staging tile: red[2][NSG][C]
+      float* red = stage;
       named_bar_sync(1, E_THREADS);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        S[slot * (C + 1) + h * 32 + i] = st_s[i];
-        SS[slot * (C + 1) + h * 32 + i] = st_ss[i];
-      }
+      *reinterpret_cast<float4*>(red + (0 * NSG + sp) * C + cg * 4) = make_float4(st_s[0].x, st_s[0].y, st_s[1].x, st_s[1].y);
+      *reinterpret_cast<float4*>(red + (1 * NSG + sp) * C + cg * 4) = make_float4(st_ss[0].x, st_ss[0].y, st_ss[1].x, st_ss[1].y);
       named_bar_sync(1, E_THREADS);
       if (et < C) {
         float s = 0.f, ss = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < TILE; ++r) { s += S[r * (C + 1) + et]; ss += SS[r * (C + 1) + et]; }
+#pragma unroll
+        for (int k = 0; k < NSG; ++k) { s += red[(0 * NSG + k) * C + et]; ss += red[(1 * NSG + k) * C + et]; }
         const float b = p.b2 ? __ldg(p.b2 + et) : 0.f;
         const float cnt = (float)(s_end - s_begin);
         // sum (acc + b) and sum (acc + b)^2 from the raw accumulator sums
@@ -411,125 +446,128 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_fused(const Params p) {
     }   // !F_Z1
   } else {
     // =========================== gather warps ============================================================
-    // Thread (gc, sl): channels 4gc .. 4gc+3 of slots sl*8 .. sl*8+7 of every tile.  The P / Q rows of tile t+1 are
-    // requested slot by slot while tile t is being computed ("rolling" register prefetch: 8 slots per thread are
-    // always in flight, across tile boundaries).  Straight-line code, 32-bit row offsets.
+    // Thread (gc, sl): channels 4gc .. 4gc+3 of slots i * NSLG + sl (i < SPT) of every tile -- the two half-warps work
+    // on adjacent slots, so their record reads share a wavefront and their a1 rows share an 8-row swizzle atom.  The
+    // P / Q rows of tile t+1 are requested slot by slot while tile t is being computed ("rolling" register prefetch:
+    // SPT slots per thread are always in flight, across tile boundaries).  Straight-line code, packed fp32 pairs.
     const int g = tid - E_THREADS, gc = g & 15, sl = g >> 4;
-    float w1c[4][4], bias1[4], sc1[4], sh1[4];
+    float2 w[4][2], bias1[2], sc1[2], sh1[2];
+    {
+      float wt[4][4], bt[4], sct[4], sht[4];
 #pragma unroll
-    for (int qq = 0; qq < 4; ++qq) {
-      const int c = gc * 4 + qq;
+      for (int qq = 0; qq < 4; ++qq) {
+        const int c = gc * 4 + qq;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) w1c[qq][k] = __ldg(p.w1c + c * p.ld1 + k);
-      bias1[qq] = p.b1 ? __ldg(p.b1 + c) : 0.f;
-      sc1[qq] = (FLAGS & F_Z1) ? 0.f : __ldg(p.stat1 + c);
-      sh1[qq] = (FLAGS & F_Z1) ? 0.f : __ldg(p.stat1 + C + c);
+        for (int k = 0; k < 4; ++k) wt[qq][k] = __ldg(p.w1c + c * p.ld1 + k);
+        bt[qq] = p.b1 ? __ldg(p.b1 + c) : 0.f;
+        sct[qq] = (FLAGS & F_Z1) ? 0.f : __ldg(p.stat1 + c);
+        sht[qq] = (FLAGS & F_Z1) ? 0.f : __ldg(p.stat1 + C + c);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        w[k][0] = make_float2(wt[0][k], wt[1][k]);
+        w[k][1] = make_float2(wt[2][k], wt[3][k]);
+      }
+      bias1[0] = make_float2(bt[0], bt[1]); bias1[1] = make_float2(bt[2], bt[3]);
+      sc1[0] = make_float2(sct[0], sct[1]); sc1[1] = make_float2(sct[2], sct[3]);
+      sh1[0] = make_float2(sht[0], sht[1]); sh1[1] = make_float2(sht[2], sht[3]);
     }
-    float z_s[4] = {0.f, 0.f, 0.f, 0.f}, z_ss[4] = {0.f, 0.f, 0.f, 0.f};     // F_Z1 accumulators
+    float2 z_s[2], z_ss[2];                                 // F_Z1 accumulators
+    z_s[0] = z_s[1] = z_ss[0] = z_ss[1] = make_float2(0.f, 0.f);
     const char* pbase = reinterpret_cast<const char*>(p.pq + gc * 4);
-    const char* qbase = reinterpret_cast<const char*>(p.pq + C + gc * 4);
-    float4 qv[8], pv[8];
+    float4 qv[SPT], pv[SPT];
     auto issue = [&](int st, int i) {
-      const int2 ds = reinterpret_cast<const int2*>(ring + st * RING_BYTES)[sl * 8 + i];
+      const int2 ds = *reinterpret_cast<const int2*>(ring + st * RING_BYTES + (i * NSLG + sl) * 16);
       // (re-loading P[dst] for every slot of a run was measured faster than de-duplicating it with a select chain)
       pv[i] = __ldg(reinterpret_cast<const float4*>(pbase + (uint32_t)ds.x));
-      qv[i] = __ldg(reinterpret_cast<const float4*>(qbase + (uint32_t)ds.y));
+      qv[i] = __ldg(reinterpret_cast<const float4*>(pbase + (uint32_t)ds.y));
     };
+    const int gw = g >> 5;                                  // gather warp index
     if (ntiles > 0) {
-      mbar_wait(smem_u32(&bar_ring_full[0]), 0u);
+      mbar_wait_park(smem_u32(&bar_ring_full[0]), 0u);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) issue(0, i);
+      for (int i = 0; i < SPT; ++i) issue(0, i);
     }
-    const int gw = g >> 5;       // gather warp index
-    int pending = -1;            // tile whose MMA this warp still has to issue
-    auto poll_issue = [&]() {    // warp-uniform
-      if (pending >= 0 && mbar_try_wait(smem_u32(&bar_a_full[pending & 1]), (uint32_t)((pending >> 1) & 1))) {
-        issue_mma(pending);
-        pending = -1;
-      }
-    };
-    // byte offset of (slot sl*8, chunk gc) in the SWIZZLE_128B K-major a1 tile; slot sl*8+i adds i*128 and flips
-    // the chunk index by i
-    const uint32_t off0 = (uint32_t)(gc >> 3) * A_KB + (uint32_t)sl * 1024u;
+    // byte offset of (row sl, chunk gc) in the SWIZZLE_128B K-major a1 tile: row r = i * NSLG + sl lives in the 8-row
+    // atom r >> 3 at row r & 7 (= sl & 7, since NSLG is a multiple of 8), its 16-byte chunk index is flipped by r & 7
+    const uint32_t off0 = (uint32_t)(gc >> 3) * A_KB + (uint32_t)(sl >> 3) * 1024u + (uint32_t)(sl & 7) * 128u +
+                          ((((uint32_t)gc & 7u) ^ ((uint32_t)sl & 7u)) << 4);
     for (int it = 0; it < ntiles; ++it) {
       const int s = it & 1;
       const int64_t s0 = s_begin + (int64_t)it * TILE;
       const int nvalid = (int)min((int64_t)TILE, s_end - s0);
-      const int st_cur = it & (RING - 1), st_next = (it + 1) & (RING - 1);
+      const int st_cur = it % RING, st_next = (it + 1) % RING;
       const bool have_next = it + 1 < ntiles;
-      if (have_next) mbar_wait(smem_u32(&bar_ring_full[st_next]), (uint32_t)(((it + 1) / RING) & 1));
-      if (!(FLAGS & F_Z1) && it >= 2) mbar_wait(smem_u32(&bar_a_empty[s]), (uint32_t)(((it >> 1) - 1) & 1));
+      if (have_next) mbar_wait_park(smem_u32(&bar_ring_full[st_next]), (uint32_t)(((it + 1) / RING) & 1));
+      if (!(FLAGS & F_Z1) && it >= 2) mbar_wait_park(smem_u32(&bar_a_empty[s]), (uint32_t)(((it >> 1) - 1) & 1));
       uint8_t* a_tile = sm + (uint32_t)s * A_STAGE;
-      const float4* attr_s = reinterpret_cast<const float4*>(ring + st_cur * RING_BYTES + TILE * 8);
+      const float4* attr_s = reinterpret_cast<const float4*>(ring + st_cur * RING_BYTES + TILE * 16);
+      if (it + PFL2 < ntiles) {
+        // L2 prefetch of the P / Q rows of tile it + PFL2 (its records are already in the ring): the register loads
+        // above run only one tile ahead of their use, which hides an L2 hit but not a DRAM miss.  Four 128-byte lines
+        // per slot, one per lane gc < 4 (P line 0 / 1, Q line 0 / 1).
+        const int st_pf = (it + PFL2) % RING;
+        mbar_wait_park(smem_u32(&bar_ring_full[st_pf]), (uint32_t)(((it + PFL2) / RING) & 1));
+        if (gc < 4) {
+          const char* pq_bytes = reinterpret_cast<const char*>(p.pq);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int slot = sl * 8 + i;
-        const float4 at = attr_s[slot];
-        const float pp[4] = {pv[i].x, pv[i].y, pv[i].z, pv[i].w};
-        const float qq4[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w};
-        float z[4];
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          float v = fmaf(at.x, w1c[qq][0], bias1[qq]);      // same association as pass A (k_edge_stats1)
-          v = fmaf(at.y, w1c[qq][1], v);
-          v = fmaf(at.z, w1c[qq][2], v);
-          v = fmaf(at.w, w1c[qq][3], v);
-          z[qq] = (v + pp[qq]) + qq4[qq];
-        }
-        if (FLAGS & F_Z1) {
-          const float m = slot < nvalid ? 1.f : 0.f;      // padding slots carry node 0's rows
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            const float v = z[qq] * m;
-            z_s[qq] += v;
-            z_ss[qq] = fmaf(v, v, z_ss[qq]);
+          for (int i = 0; i < SPT; ++i) {
+            const int2 ds = *reinterpret_cast<const int2*>(ring + st_pf * RING_BYTES + (i * NSLG + sl) * 16);
+            const uint32_t off = (uint32_t)((gc & 2) ? ds.y : ds.x) + (uint32_t)(gc & 1) * 128u;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pq_bytes + off));
           }
-          if (have_next) issue(st_next, i);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < SPT; ++i) {
+        const int slot = i * NSLG + sl;
+        const float4 at = attr_s[slot];
+        // same association in every pass: ((W1c attr + b1) + P) + Q
+        float2 v0 = ffma2s(at.x, w[0][0], bias1[0]), v1 = ffma2s(at.x, w[0][1], bias1[1]);
+        v0 = ffma2s(at.y, w[1][0], v0); v1 = ffma2s(at.y, w[1][1], v1);
+        v0 = ffma2s(at.z, w[2][0], v0); v1 = ffma2s(at.z, w[2][1], v1);
+        v0 = ffma2s(at.w, w[3][0], v0); v1 = ffma2s(at.w, w[3][1], v1);
+        v0 = fadd2(fadd2(v0, make_float2(pv[i].x, pv[i].y)), make_float2(qv[i].x, qv[i].y));
+        v1 = fadd2(fadd2(v1, make_float2(pv[i].z, pv[i].w)), make_float2(qv[i].z, qv[i].w));
+        if (have_next) issue(st_next, i);                 // refill this register slot for the next tile
+        if (FLAGS & F_Z1) {
+          if (slot < nvalid) {                            // padding slots carry stale rows
+            z_s[0] = fadd2(z_s[0], v0); z_s[1] = fadd2(z_s[1], v1);
+            z_ss[0] = ffma2(v0, v0, z_ss[0]); z_ss[1] = ffma2(v1, v1, z_ss[1]);
+          }
           continue;
         }
         if ((FLAGS & F_TAPE) && slot < nvalid)
-          *reinterpret_cast<float4*>(p.z1 + (s0 + slot) * C + gc * 4) = make_float4(z[0], z[1], z[2], z[3]);
-        float4 a1;
-        a1.x = fmaxf(fmaf(z[0], sc1[0], sh1[0]), 0.f);
-        a1.y = fmaxf(fmaf(z[1], sc1[1], sh1[1]), 0.f);
-        a1.z = fmaxf(fmaf(z[2], sc1[2], sh1[2]), 0.f);
-        a1.w = fmaxf(fmaf(z[3], sc1[3], sh1[3]), 0.f);
-        const uint32_t off = off0 + (uint32_t)i * 128u + (uint32_t)(((gc & 7) ^ i) << 4);
-        store_split_fast(a_tile, a_tile + A_HI, off, a1);   // a1 >= 0 and finite
-        if (have_next) issue(st_next, i);                 // refill this register slot for the next tile
-        if (i & 1) poll_issue();
+          *reinterpret_cast<float4*>(p.z1 + (s0 + slot) * C + gc * 4) = make_float4(v0.x, v0.y, v1.x, v1.y);
+        float2 a0 = ffma2(v0, sc1[0], sh1[0]), a1 = ffma2(v1, sc1[1], sh1[1]);
+        a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f); a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f);
+        store_split_trunc(a_tile, a_tile + A_HI, off0 + (uint32_t)(i * (NSLG / 8)) * 1024u, a0, a1);   // a1 >= 0, finite
       }
       if (FLAGS & F_Z1) {
-        mbar_arrive(smem_u32(&bar_ring_empty[st_cur]));
+        warp_arrive(smem_u32(&bar_ring_empty[st_cur]), lane);
         continue;
       }
       fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the tensor core
-      mbar_arrive(smem_u32(&bar_a_full[s]));
-      mbar_arrive(smem_u32(&bar_ring_empty[st_cur]));     // idx (read one tile ago) and attr of this tile are consumed
-      if (pending >= 0) {                                 // (only if this warp ran a whole tile ahead of the others)
-        mbar_wait(smem_u32(&bar_a_full[pending & 1]), (uint32_t)((pending >> 1) & 1));
-        issue_mma(pending);
-        pending = -1;
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&bar_a_full[s]));
+        mbar_arrive(smem_u32(&bar_ring_empty[st_cur]));   // idx (read one tile ago) and attr of this tile are consumed
       }
-      if (gw == (it & (G_WARPS - 1))) pending = it;
-    }
-    if (pending >= 0) {                                   // the last tile
-      mbar_wait(smem_u32(&bar_a_full[pending & 1]), (uint32_t)((pending >> 1) & 1));
-      issue_mma(pending);
-    }
-    if (FLAGS & F_Z1) {                                   // combine the 16 slot groups; part = [sum | sum of squares]
-      float* red = reinterpret_cast<float*>(sm);          // [2][16][C], the a1 ring is unused in this pass
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        red[(0 * 16 + sl) * C + gc * 4 + qq] = z_s[qq];
-        red[(1 * 16 + sl) * C + gc * 4 + qq] = z_ss[qq];
+      if (MMA_G && gw == it % G_WARPS) {
+        __syncwarp();
+        issue_mma(it);
       }
+    }
+    if (FLAGS & F_Z1) {                                   // combine the slot groups; part = [sum | sum of squares]
+      float* red = reinterpret_cast<float*>(sm);          // [2][NSLG][C], the a1 ring is unused in this pass
+      *reinterpret_cast<float4*>(red + (0 * NSLG + sl) * C + gc * 4) = make_float4(z_s[0].x, z_s[0].y, z_s[1].x, z_s[1].y);
+      *reinterpret_cast<float4*>(red + (1 * NSLG + sl) * C + gc * 4) = make_float4(z_ss[0].x, z_ss[0].y, z_ss[1].x, z_ss[1].y);
       named_bar_sync(2, G_THREADS);
       if (g < 2 * C) {
         const int which = g / C, c = g % C;
         float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc += red[(which * 16 + k) * C + c];
+        for (int k = 0; k < NSLG; ++k) acc += red[(which * NSLG + k) * C + c];
         p.part[((int64_t)blockIdx.x * 2 + which) * C + c] = acc;
       }
     }
@@ -540,16 +578,56 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_fused(const Params p) {
   if (warp == 0) tmem_dealloc(tmem_d, 2 * C);
 }
 
-template <int FLAGS>
-static cudaError_t launch(const Params& p, int grid, cudaStream_t st) {
+// Slot-ordered records of one layer call: P / Q byte offsets (Q relative to the P base, i.e. + C floats) | eid, and the
+// attribute row of the slot's edge.  16 bytes each so that any slot range is a legal TMA bulk copy.
+__global__ void k_edge_records(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                               const int32_t* __restrict__ eid, const float4* __restrict__ attr, int64_t E,
+                               uint32_t ldpq_b, int4* __restrict__ rec_idx, float4* __restrict__ rec_attr) {
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= E) return;
+  const int e = __ldg(eid + s);
+  rec_idx[s] = make_int4((int)((uint32_t)__ldg(dst + s) * ldpq_b), (int)((uint32_t)__ldg(src + s) * ldpq_b + (uint32_t)C * 4u), e, 0);
+  rec_attr[s] = __ldg(attr + e);
+}
+
+// Role split: YOLAT_EF_ROLES = "8x8" (default) or "4x16" epilogue x gather warps (a tuning knob, all CUDA).
+static int roles() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YOLAT_EF_ROLES");
+    v = 1;
+    if (e && e[0] == '4') v = 0;
+  }
+  return v;
+}
+
+template <int FLAGS, int EW, int GW, bool MG>
+static cudaError_t launch_cfg(const Params& p, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_edge_fused<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_edge_fused<FLAGS, EW, GW, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  k_edge_fused<FLAGS><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+  k_edge_fused<FLAGS, EW, GW, MG><<<grid, (EW + GW) * 32, SMEM_BYTES, st>>>(p);
   return cudaSuccess;
+}
+
+// Who issues the MMAs: the role that is not the bottleneck of the pass.  Measured at N = 320 000, E = 1 280 000 (8x8):
+// F_STATS 144 us (epilogue issues) vs 163 us (gather issues); F_AGG 237 us vs 187 us.  YOLAT_EF_MG = 0 / 1 forces one.
+static int mma_by_gather(int flags) {
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("YOLAT_EF_MG"); v = e ? atoi(e) : -1; }
+  return v >= 0 ? v : ((flags & F_AGG) ? 1 : 0);
+}
+
+template <int FLAGS>
+static cudaError_t launch(const Params& p, int grid, cudaStream_t st) {
+  const bool mg = mma_by_gather(FLAGS) != 0;
+  switch (roles()) {
+    case 1: return mg ? launch_cfg<FLAGS, 8, 8, true>(p, grid, st) : launch_cfg<FLAGS, 8, 8, false>(p, grid, st);
+    default: return mg ? launch_cfg<FLAGS, 4, 16, true>(p, grid, st) : launch_cfg<FLAGS, 4, 16, false>(p, grid, st);
+  }
 }
 
 }  // namespace ef
@@ -560,19 +638,38 @@ bool edge_fused_fits(int64_t N, int64_t ldpq) { return N * ldpq < (1ll << 30); }
 
 int edge_fused_grid(int64_t E) {
   const int64_t tiles = cdiv(E > 0 ? E : 1, ef::TILE);
-  const int64_t cap = (int64_t)kNumSMs;           // persistent: one CTA (17 warps, ~200 KB of shared memory) per SM
+  const int64_t cap = (int64_t)kNumSMs;           // persistent: one CTA (~220 KB of shared memory) per SM
   return (int)(tiles < cap ? tiles : cap);
 }
 
 int edge_stats1_grid(int64_t E) { return edge_fused_grid(E); }
 
+// floats of workspace for the slot-ordered records of one layer call (8 per slot)
+int64_t edge_records_floats(int64_t E) { return 8 * (E > 0 ? E : 0) + 8; }
+
+// rec: [edge_records_floats(E)] floats, 16-byte aligned (the arena is): int4 records first, float4 attribute rows after
+int edge_records(const GraphView& g, int64_t E, const float* attr, int64_t ldpq, float* rec, cudaStream_t st) {
+  if (E <= 0) return YOLAT_OK;
+  int4* ri = reinterpret_cast<int4*>(rec);
+  float4* ra = reinterpret_cast<float4*>(rec + 4 * E);
+  ef::k_edge_records<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(g.src_t, g.dst_t, g.eid_t, reinterpret_cast<const float4*>(attr), E,
+                                                             (uint32_t)ldpq * 4u, ri, ra);
+  YOLAT_CHECK_LAUNCH();
+  return YOLAT_OK;
+}
+
+static void set_records(ef::Params& p, const float* rec, int64_t E) {
+  p.rec_idx = reinterpret_cast<const int4*>(rec);
+  p.rec_attr = reinterpret_cast<const float4*>(rec + 4 * E);
+}
+
 // part: [edge_stats1_grid(E)][2][C] sums / sums of squares of z1 over all edges
-int edge_stats1(const GraphView& g, int64_t N, int64_t E, const float* pq, int64_t ldpq, const float* attr,
+int edge_stats1(const GraphView& g, int64_t N, int64_t E, const float* pq, int64_t ldpq, const float* rec,
                 const float* w1, int Cin, const float* b1, float* part, cudaStream_t st) {
   if (E <= 0) return YOLAT_OK;
   ef::Params p{};
   p.rowptr = g.rowptr_t; p.src = g.src_t; p.dst = g.dst_t; p.eid = g.eid_t; p.deg_inv = g.deg_inv;
-  p.N = N; p.E = E; p.pq = pq; p.ldpq = (uint32_t)ldpq; p.attr = attr;
+  p.N = N; p.E = E; p.pq = pq; p.ldpq = (uint32_t)ldpq; set_records(p, rec, E);
   p.w1c = w1 + 2 * Cin; p.ld1 = 2 * Cin + 4; p.b1 = b1; p.part = part;
   ProfScope prof(YOLAT_PROF_EDGE_STATS1, st);
   cudaError_t e = ef::launch<ef::F_Z1>(p, edge_fused_grid(E), st);
@@ -582,14 +679,14 @@ int edge_stats1(const GraphView& g, int64_t N, int64_t E, const float* pq, int64
 }
 
 // flags: EF_TAPE | EF_STATS | EF_AGG (common.cuh).  part: [edge_fused_grid(E)][2][C] when EF_STATS.
-int edge_fused(const GraphView& g, int64_t N, int64_t E, int flags, const float* pq, int64_t ldpq, const float* attr,
+int edge_fused(const GraphView& g, int64_t N, int64_t E, int flags, const float* pq, int64_t ldpq, const float* rec,
                const float* w1, int Cin, const float* b1, const float* stat1, const float* w2, const float* b2,
                const float* stat2, const float* ew, float* z1, float* z2, float* part, const float* base, int64_t ldb,
                float* out, int64_t ldo, cudaStream_t st) {
   if (E <= 0) return YOLAT_OK;
   ef::Params p{};
   p.rowptr = g.rowptr_t; p.src = g.src_t; p.dst = g.dst_t; p.eid = g.eid_t; p.deg_inv = g.deg_inv;
-  p.N = N; p.E = E; p.pq = pq; p.ldpq = (uint32_t)ldpq; p.attr = attr;
+  p.N = N; p.E = E; p.pq = pq; p.ldpq = (uint32_t)ldpq; set_records(p, rec, E);
   p.w1c = w1 + 2 * Cin; p.ld1 = 2 * Cin + 4;
   p.b1 = b1; p.stat1 = stat1; p.w2 = w2; p.b2 = b2; p.stat2 = stat2; p.ew = ew;
   p.z1 = z1; p.z2 = z2; p.part = part; p.base = base; p.ldb = ldb; p.out = out; p.ldo = ldo;

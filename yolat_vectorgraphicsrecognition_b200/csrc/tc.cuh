@@ -49,6 +49,35 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t addr, uint32_t parity) 
     if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
   }
 }
+// Waits that leave the issue slots to the working warps: try_wait with a suspend-time hint parks the warp in hardware
+// until the phase completes (wake-up ~60 cycles after the arrive) or the hint expires.  Bounded like mbar_wait.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t addr, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_park(uint32_t addr, uint32_t parity) {
+  if (mbar_try_wait(addr, parity)) return;
+  for (int spins = 0; !mbar_try_wait_hint(addr, parity, 1000000u); ++spins) {
+    if (spins > 20000000) asm volatile("trap;");
+  }
+}
+// ---- TMA bulk copy (cp.async.bulk, 1-D): global -> shared, completion counted in bytes on an mbarrier -------------
+__device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+// dst / src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
 // one lane of a fully converged warp; keeps the guarded region in the uniform datapath (descriptors in UR registers)
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;
@@ -148,6 +177,52 @@ __device__ __forceinline__ void store_split(uint8_t* hi_base, uint8_t* lo_base, 
   split_tf32(v.w, h.w, l.w);
   *reinterpret_cast<float4*>(hi_base + off) = h;
   *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+
+
+// ---- packed fp32 pairs (FFMA2 / FADD2 on sm_100: two fp32 lanes per instruction, each lane IEEE round-to-nearest) ----
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2s(float s, float2 b, float2 c) { return ffma2(make_float2(s, s), b, c); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "sub.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+// Truncating split of a non-negative finite value for 3xTF32: hi = the top 19 bits (exactly what the tensor core
+// reads of a tf32 operand), lo = x - hi exactly (13 significant bits).  One LOP3 + half an FADD2 per value.
+__device__ __forceinline__ void store_split_trunc(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float2 a, float2 b) {
+  float4 h;
+  h.x = __uint_as_float(__float_as_uint(a.x) & 0xffffe000u);
+  h.y = __uint_as_float(__float_as_uint(a.y) & 0xffffe000u);
+  h.z = __uint_as_float(__float_as_uint(b.x) & 0xffffe000u);
+  h.w = __uint_as_float(__float_as_uint(b.y) & 0xffffe000u);
+  const float2 l0 = fsub2(a, make_float2(h.x, h.y)), l1 = fsub2(b, make_float2(h.z, h.w));
+  *reinterpret_cast<float4*>(hi_base + off) = h;
+  *reinterpret_cast<float4*>(lo_base + off) = make_float4(l0.x, l0.y, l1.x, l1.y);
 }
 
 }  // namespace tc
