@@ -108,8 +108,9 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
   constexpr int SPT = TILE * 16 / G_THREADS;              // slots per gather thread and tile (16 threads per slot)
   constexpr int NSLG = TILE / SPT;                        // slot groups: slot = i * NSLG + sl
   constexpr int NSG = E_THREADS / 16;                     // F_STATS: slot groups of the column sums
-  constexpr int TPR = 4;                                  // F_AGG: threads per target row
-  constexpr int RIF = E_THREADS / TPR;                    // F_AGG: rows in flight (their bookkeeping is prefetched)
+  constexpr int TPR = E_THREADS / 32;                     // F_AGG: threads per target row
+  constexpr int RIF = 32;                                 // F_AGG: rows per sweep of the epilogue threads
+  constexpr int NPF = 2;                                  // F_AGG: sweeps whose row bookkeeping is prefetched a tile ahead
   constexpr int CPT = 16 / TPR;                           // F_AGG: 16-byte chunks per thread (chunk k at ch + 4 TPR k)
   static_assert(E_WARPS == 4 || E_WARPS == 8, "epilogue mapping");
   static_assert(SPT * G_THREADS == TILE * 16 && (SPT == 4 || SPT == 8), "gather mapping");
@@ -257,9 +258,11 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
     const int rl = et / TPR;                         // row lane: 0 .. RIF - 1
     int R_prev = r_begin;
     int R_cur = 0;
-    int nb = 0, ne_ = 0;                             // rowptr[r], rowptr[r + 1] of this thread's first row of the tile
-    float ndi = 0.f;
-    float4 nbase[CPT];
+    int nb[NPF], ne_[NPF];                           // rowptr[r], rowptr[r + 1] of this thread's first NPF rows of the tile
+    float ndi[NPF];
+    float4 nbase[NPF][CPT];
+#pragma unroll
+    for (int q2 = 0; q2 < NPF; ++q2) { nb[q2] = 0; ne_[q2] = 0; ndi[q2] = 0.f; }
     auto row_meta = [&](int r, int& b, int& e, float& di, float4 (&bs)[CPT], bool want) {
       b = 0; e = 0; di = 0.f;
 #pragma unroll
@@ -281,10 +284,17 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
     };
     if ((FLAGS & F_AGG) && ntiles > 0) {
       R_cur = tile_rcur(0);
-      row_meta(R_prev + rl, nb, ne_, ndi, nbase, true);
+#pragma unroll
+      for (int q2 = 0; q2 < NPF; ++q2) row_meta(R_prev + rl + q2 * RIF, nb[q2], ne_[q2], ndi[q2], nbase[q2], true);
     }
 
     if (!MMA_G && warp == 0 && ntiles > 0) issue_mma(0);
+    constexpr bool SH_REG = FOLD && E_WARPS == 8;    // one column half per thread: its BN2 shifts live in registers
+    float shr[SH_REG ? 32 : 1];
+    if (SH_REG) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) shr[SH_REG ? i : 0] = bn2_s[C + h_begin * 32 + i];
+    }
     for (int t = 0; t < ntiles; ++t) {
       if (producer) fill(t + PF);                    // never blocks in practice: the gather finished tile t - 1 long ago
       if (!MMA_G && warp == 0 && t + 1 < ntiles) issue_mma(t + 1);
@@ -325,7 +335,9 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
         if (FLAGS & F_AGG) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float4 sh = *reinterpret_cast<const float4*>(bn2_s + C + h * 32 + i);
+            float4 sh;
+            if (SH_REG) sh = make_float4(shr[SH_REG ? i : 0], shr[SH_REG ? i + 1 : 0], shr[SH_REG ? i + 2 : 0], shr[SH_REG ? i + 3 : 0]);
+            else sh = *reinterpret_cast<const float4*>(bn2_s + C + h * 32 + i);
             float4 m;
             if (FOLD) {
               m.x = fmaxf(v[i] + sh.x, 0.f);
@@ -365,18 +377,23 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
         const bool last = s1 >= s_end;
         const float* cin = carry + (t & 1) * C;
         float* cout = carry + ((t + 1) & 1) * C;
-        int b = nb, e = ne_;
-        float di = ndi;
-        float4 bs[CPT];
+        int cb[NPF], ce[NPF];
+        float cdi[NPF];
+        float4 cbs[NPF][CPT];
 #pragma unroll
-        for (int k = 0; k < CPT; ++k) bs[k] = nbase[k];
+        for (int q2 = 0; q2 < NPF; ++q2) {
+          cb[q2] = nb[q2]; ce[q2] = ne_[q2]; cdi[q2] = ndi[q2];
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) cbs[q2][k] = nbase[q2][k];
+        }
         const int R_next = (t + 1 < ntiles) ? tile_rcur(t + 1) : r_end;      // used one tile later
-        row_meta(R_cur + rl, nb, ne_, ndi, nbase, t + 1 < ntiles);           // first row of the next tile
-        for (int r = R_prev + rl; r <= R_cur; r += RIF) {
-          if (r == R_cur && last) break;
-          if (r != R_prev + rl) row_meta(r, b, e, di, bs, true);
+#pragma unroll
+        for (int q2 = 0; q2 < NPF; ++q2)                                     // the first rows of the next tile
+          row_meta(R_cur + rl + q2 * RIF, nb[q2], ne_[q2], ndi[q2], nbase[q2], t + 1 < ntiles);
+        auto reduce_row = [&](int r, int b, int e, float di, const float4 (&bs)[CPT]) {
+          if (r > R_cur || (r == R_cur && last)) return;
           const bool done = r < R_cur;
-          if (!done && (int64_t)b >= s1) break;     // the next row starts exactly at the tile boundary: nothing to carry
+          if (!done && (int64_t)b >= s1) return;    // the next row starts exactly at the tile boundary: nothing to carry
           float2 acc[2 * CPT];
 #pragma unroll
           for (int k = 0; k < 2 * CPT; ++k) acc[k] = make_float2(0.f, 0.f);
@@ -410,6 +427,15 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
               *reinterpret_cast<float4*>(cout + ch + 4 * TPR * k) =
                   make_float4(acc[2 * k].x, acc[2 * k].y, acc[2 * k + 1].x, acc[2 * k + 1].y);
           }
+        };
+#pragma unroll
+        for (int q2 = 0; q2 < NPF; ++q2) reduce_row(R_prev + rl + q2 * RIF, cb[q2], ce[q2], cdi[q2], cbs[q2]);
+        for (int r = R_prev + rl + NPF * RIF; r <= R_cur; r += RIF) {        // tiles of many short rows (rare)
+          int b, e;
+          float di;
+          float4 bs[CPT];
+          row_meta(r, b, e, di, bs, true);
+          reduce_row(r, b, e, di, bs);
         }
         R_prev = R_cur;
         R_cur = R_next;

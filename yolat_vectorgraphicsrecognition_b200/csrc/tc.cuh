@@ -65,7 +65,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t addr, uint32_t p
 __device__ __forceinline__ void mbar_wait_park(uint32_t addr, uint32_t parity) {
   if (mbar_try_wait(addr, parity)) return;
   for (int spins = 0; !mbar_try_wait_hint(addr, parity, 1000000u); ++spins) {
-    if (spins > 20000000) asm volatile("trap;");
+    if (spins > 200000000) asm volatile("trap;");
   }
 }
 // ---- TMA bulk copy (cp.async.bulk, 1-D): global -> shared, completion counted in bytes on an mbarrier -------------
