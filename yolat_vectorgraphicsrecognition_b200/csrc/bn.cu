@@ -257,6 +257,93 @@ __global__ void k_bn_bwd_apply(BnBwdArgs a, const float* __restrict__ bstat) {
   a.dz[r * a.lddz + c] = sc * (dy - bstat[c] - xhat * bstat[a.C + c]);
 }
 
+// ---- four columns per thread (C % 4 == 0, 16-byte aligned rows): 128-bit accesses, one row
+//      look-up per thread instead of per element ----------------------------------------------------------------------
+template <bool NC>   // NC: gy is read-only for the whole kernel (the apply pass may run in place on gy)
+__device__ __forceinline__ float4 bwd_load_dy4(const BnBwdArgs& a, int64_t r, int c) {
+  const int64_t row = a.row_idx ? (int64_t)__ldg(a.row_idx + r) : r;
+  const float4* gp = reinterpret_cast<const float4*>(a.gy + row * a.ldgy + c);
+  float4 v = NC ? __ldg(gp) : *gp;
+  float f = 1.f;
+  if (a.row_scale) f = __ldg(a.row_scale + row);
+  if (a.slot_scale) f *= __ldg(a.slot_scale + (a.slot_idx ? __ldg(a.slot_idx + r) : r));
+  if (a.row_scale || a.slot_scale) { v.x *= f; v.y *= f; v.z *= f; v.w *= f; }
+  return v;
+}
+
+// part: [nparts][2][C]; 256 threads = 16 row lanes x 16 column groups (64 columns), grid (ceil(C4 / 16), nparts)
+__global__ void __launch_bounds__(256) k_bn_bwd_partial4(BnBwdArgs a, int C4, float* __restrict__ part) {
+  __shared__ float4 s1[256], s2[256];
+  const int cg = blockIdx.x * 16 + (threadIdx.x & 15), rl = threadIdx.x >> 4;
+  const int c = cg * 4;
+  const int64_t r0 = (int64_t)blockIdx.y * ST_ROWS_PER_CTA;
+  const int64_t r1 = min(a.M, r0 + ST_ROWS_PER_CTA);
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = p;
+  if (cg < C4) {
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.stat + c)), sh = __ldg(reinterpret_cast<const float4*>(a.stat + a.C + c));
+    const float4 mean = __ldg(reinterpret_cast<const float4*>(a.stat + 2 * a.C + c));
+    const float4 invstd = __ldg(reinterpret_cast<const float4*>(a.stat + 3 * a.C + c));
+#pragma unroll 4
+    for (int64_t r = r0 + rl; r < r1; r += 16) {
+      const float4 zz = __ldg(reinterpret_cast<const float4*>(a.z + r * a.ldz + c));
+      float4 dy = bwd_load_dy4<true>(a, r, c);
+      if (a.relu) {
+        if (!(fmaf(zz.x, sc.x, sh.x) > 0.f)) dy.x = 0.f;
+        if (!(fmaf(zz.y, sc.y, sh.y) > 0.f)) dy.y = 0.f;
+        if (!(fmaf(zz.z, sc.z, sh.z) > 0.f)) dy.z = 0.f;
+        if (!(fmaf(zz.w, sc.w, sh.w) > 0.f)) dy.w = 0.f;
+      }
+      p.x += dy.x; p.y += dy.y; p.z += dy.z; p.w += dy.w;
+      q.x = fmaf(dy.x, (zz.x - mean.x) * invstd.x, q.x);
+      q.y = fmaf(dy.y, (zz.y - mean.y) * invstd.y, q.y);
+      q.z = fmaf(dy.z, (zz.z - mean.z) * invstd.z, q.z);
+      q.w = fmaf(dy.w, (zz.w - mean.w) * invstd.w, q.w);
+    }
+  }
+  s1[threadIdx.x] = p; s2[threadIdx.x] = q;
+  __syncthreads();
+  if (rl == 0 && cg < C4) {
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+      const float4 u = s1[k * 16 + (threadIdx.x & 15)], v = s2[k * 16 + (threadIdx.x & 15)];
+      p.x += u.x; p.y += u.y; p.z += u.z; p.w += u.w;
+      q.x += v.x; q.y += v.y; q.z += v.z; q.w += v.w;
+    }
+    *reinterpret_cast<float4*>(part + ((int64_t)blockIdx.y * 2 + 0) * a.C + c) = p;
+    *reinterpret_cast<float4*>(part + ((int64_t)blockIdx.y * 2 + 1) * a.C + c) = q;
+  }
+}
+
+__global__ void k_bn_bwd_apply4(BnBwdArgs a, int C4, const float* __restrict__ bstat) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= a.M * C4) return;
+  const int64_t r = idx / C4;
+  const int c = (int)(idx - r * C4) * 4;
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(a.stat + c)), sh = __ldg(reinterpret_cast<const float4*>(a.stat + a.C + c));
+  const float4 mean = __ldg(reinterpret_cast<const float4*>(a.stat + 2 * a.C + c));
+  const float4 invstd = __ldg(reinterpret_cast<const float4*>(a.stat + 3 * a.C + c));
+  const float4 m1 = __ldg(reinterpret_cast<const float4*>(bstat + c)), m2 = __ldg(reinterpret_cast<const float4*>(bstat + a.C + c));
+  const float4 zz = *reinterpret_cast<const float4*>(a.z + r * a.ldz + c);     // may alias dz: plain load
+  float4 dy = bwd_load_dy4<false>(a, r, c);
+  if (a.relu) {
+    if (!(fmaf(zz.x, sc.x, sh.x) > 0.f)) dy.x = 0.f;
+    if (!(fmaf(zz.y, sc.y, sh.y) > 0.f)) dy.y = 0.f;
+    if (!(fmaf(zz.z, sc.z, sh.z) > 0.f)) dy.z = 0.f;
+    if (!(fmaf(zz.w, sc.w, sh.w) > 0.f)) dy.w = 0.f;
+  }
+  *reinterpret_cast<float4*>(a.dz + r * a.lddz + c) =
+      make_float4(sc.x * (dy.x - m1.x - (zz.x - mean.x) * invstd.x * m2.x), sc.y * (dy.y - m1.y - (zz.y - mean.y) * invstd.y * m2.y),
+                  sc.z * (dy.z - m1.z - (zz.z - mean.z) * invstd.z * m2.z), sc.w * (dy.w - m1.w - (zz.w - mean.w) * invstd.w * m2.w));
+}
+
+static bool bn_bwd_vec_ok(const BnBwdArgs& a) {
+  if (a.C % 4 != 0) return false;
+  if ((a.ldz | a.ldgy | (a.dz ? a.lddz : 0)) % 4 != 0) return false;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(a.z) | reinterpret_cast<uintptr_t>(a.gy) | reinterpret_cast<uintptr_t>(a.stat) |
+                         reinterpret_cast<uintptr_t>(a.dz);
+  return (bits & 15u) == 0;
+}
+
 int bn_bwd_finalize(const float* part, int nparts, int64_t M, int C, const float* stat, const float* gamma, int training,
                     float* bstat, float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
   k_bn_bwd_finalize<<<(unsigned)cdiv(C, 32), dim3(32, 32), 0, st>>>(part, nparts, M, C, stat, gamma, training, bstat, dgamma,
@@ -271,12 +358,18 @@ int bn_backward(const BnBwdArgs& a, Arena& ws, cudaStream_t st) {
   float* bstat = ws.take(2 * a.C);
   if (ws.dry()) return YOLAT_OK;
   if (ws.overflow) return YOLAT_ERR_WORKSPACE;
-  dim3 grid((unsigned)cdiv(a.C, ST_COLS), nparts);
-  k_bn_bwd_partial<<<grid, ST_COLS * ST_ROWS, 0, st>>>(a, part);
+  const bool vec = bn_bwd_vec_ok(a) && ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(bstat)) & 15u) == 0;
+  if (vec) {
+    k_bn_bwd_partial4<<<dim3((unsigned)cdiv(a.C / 4, 16), nparts), 256, 0, st>>>(a, a.C / 4, part);
+  } else {
+    dim3 grid((unsigned)cdiv(a.C, ST_COLS), nparts);
+    k_bn_bwd_partial<<<grid, ST_COLS * ST_ROWS, 0, st>>>(a, part);
+  }
   YOLAT_CHECK_LAUNCH();
   YOLAT_TRY(bn_bwd_finalize(part, nparts, a.M, a.C, a.stat, a.gamma, a.training, bstat, a.dgamma, a.dbeta, a.dbias, st));
   if (a.M * a.C > 0 && a.dz) {
-    k_bn_bwd_apply<<<(unsigned)cdiv(a.M * a.C, 256), 256, 0, st>>>(a, bstat);
+    if (vec) k_bn_bwd_apply4<<<(unsigned)cdiv(a.M * (a.C / 4), 256), 256, 0, st>>>(a, a.C / 4, bstat);
+    else k_bn_bwd_apply<<<(unsigned)cdiv(a.M * a.C, 256), 256, 0, st>>>(a, bstat);
     YOLAT_CHECK_LAUNCH();
   }
   return YOLAT_OK;

@@ -75,8 +75,8 @@ __global__ void k_zero_strided(float* __restrict__ p, int64_t ld, int64_t M, int
 }
 
 // ---- fusion backward: the post-ReLU gradient is sparse (one row per (segment, column)) --------------
-// partial sums over segments of dy' and dy'*xhat; part [nparts][2][F]; rows-per-CTA = 256 segments
-constexpr int FM_SEGS_PER_CTA = 256;
+// partial sums over segments of dy' and dy'*xhat; part [nparts][2][F]; FM_SEGS_PER_CTA segments per CTA
+constexpr int FM_SEGS_PER_CTA = 32;    // 4 dependent (arg -> z) look-ups per thread: the chain is latency-bound, so spread it
 __global__ void __launch_bounds__(256) k_fusemax_bwd_partial(const float* __restrict__ gp, int64_t ldg, int F, int64_t S,
                                                              const int32_t* __restrict__ arg, int64_t lda,
                                                              const float* __restrict__ z, const float* __restrict__ stat,
@@ -122,6 +122,38 @@ __global__ void k_fusemax_bwd_apply(float* __restrict__ z, int64_t M, int F, con
   float dy = 0.f;
   if (s >= 0 && arg[(int64_t)s * lda + c] == (int32_t)n && fmaf(zz, sc, sh) > 0.f) dy = gp[(int64_t)s * ldg + c];
   z[idx] = sc * (dy - bstat[c] - (zz - mean) * invstd * bstat[F + c]);
+}
+
+// Same, four columns per thread (F % 4 == 0, 16-byte aligned rows): 128-bit loads / stores, one row look-up per thread.
+__global__ void k_fusemax_bwd_apply4(float* __restrict__ z, int64_t M, int F4, const int32_t* __restrict__ seg_of_row,
+                                     const float* __restrict__ gp, int64_t ldg, const int32_t* __restrict__ arg,
+                                     int64_t lda, const float* __restrict__ stat, const float* __restrict__ bstat) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= M * F4) return;
+  const int64_t n = idx / F4;
+  const int c = (int)(idx - n * F4) * 4;
+  const int F = F4 * 4;
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(stat + c)), sh = __ldg(reinterpret_cast<const float4*>(stat + F + c));
+  const float4 mean = __ldg(reinterpret_cast<const float4*>(stat + 2 * F + c));
+  const float4 invstd = __ldg(reinterpret_cast<const float4*>(stat + 3 * F + c));
+  const float4 m1 = __ldg(reinterpret_cast<const float4*>(bstat + c)), m2 = __ldg(reinterpret_cast<const float4*>(bstat + F + c));
+  float4* zp = reinterpret_cast<float4*>(z + n * F + c);
+  const float4 zz = *zp;
+  const int32_t s = __ldg(seg_of_row + n);
+  float4 dy = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s >= 0) {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(arg + (int64_t)s * lda + c));
+    const int32_t nn = (int32_t)n;
+    if (a.x == nn || a.y == nn || a.z == nn || a.w == nn) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gp + (int64_t)s * ldg + c));
+      if (a.x == nn && fmaf(zz.x, sc.x, sh.x) > 0.f) dy.x = g.x;
+      if (a.y == nn && fmaf(zz.y, sc.y, sh.y) > 0.f) dy.y = g.y;
+      if (a.z == nn && fmaf(zz.z, sc.z, sh.z) > 0.f) dy.z = g.z;
+      if (a.w == nn && fmaf(zz.w, sc.w, sh.w) > 0.f) dy.w = g.w;
+    }
+  }
+  *zp = make_float4(sc.x * (dy.x - m1.x - (zz.x - mean.x) * invstd.x * m2.x), sc.y * (dy.y - m1.y - (zz.y - mean.y) * invstd.y * m2.y),
+                    sc.z * (dy.z - m1.z - (zz.z - mean.z) * invstd.z * m2.z), sc.w * (dy.w - m1.w - (zz.w - mean.w) * invstd.w * m2.w));
 }
 
 // ---- CrossEntropyLoss (mean) -----------------------------------------------------------------------
@@ -231,6 +263,14 @@ int fusemax_bwd_partial_launch(const float* gp, int64_t ldg, int F, int64_t S, c
 int fusemax_bwd_apply_launch(float* z, int64_t M, int F, const int32_t* seg_of_row, const float* gp, int64_t ldg,
                              const int32_t* arg, int64_t lda, const float* stat, const float* bstat, cudaStream_t st) {
   if (M * F <= 0) return YOLAT_OK;
+  const bool vec = (F % 4 == 0) && (ldg % 4 == 0) && (lda % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(gp) | reinterpret_cast<uintptr_t>(arg) |
+                     reinterpret_cast<uintptr_t>(stat) | reinterpret_cast<uintptr_t>(bstat)) & 15u) == 0;
+  if (vec) {
+    k_fusemax_bwd_apply4<<<(unsigned)cdiv(M * (F / 4), 256), 256, 0, st>>>(z, M, F / 4, seg_of_row, gp, ldg, arg, lda, stat, bstat);
+    YOLAT_CHECK_LAUNCH();
+    return YOLAT_OK;
+  }
   k_fusemax_bwd_apply<<<(unsigned)cdiv(M * F, 256), 256, 0, st>>>(z, M, F, seg_of_row, gp, ldg, arg, lda, stat, bstat);
   YOLAT_CHECK_LAUNCH();
   return YOLAT_OK;
