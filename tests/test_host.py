@@ -94,3 +94,24 @@ def test_shard_graphs():
     edges = [10, 10, 10, 70, 10, 10, 10, 10]
     parts = [dp.shard_graphs(8, 2, r, edges) for r in range(2)]
     assert parts == [(0, 4), (4, 8)]
+
+
+def test_packed_batch_layout_roundtrip():
+    """batch.PackedBatch: six fields in one buffer, 256-byte aligned sections, views alias the buffer."""
+    import torch
+    from yolat_vectorgraphicsrecognition_b200 import synth
+    from yolat_vectorgraphicsrecognition_b200.batch import FIELDS, PackedBatch
+    b = synth.floorplans_batch(graphs=2, n=100, e=300, seed=3)
+    pb = PackedBatch.from_batch(b, pin=False)
+    assert pb.host.dtype == torch.uint8 and pb.nbytes == pb.host.numel()
+    for name, off, nbytes, shape, dtype in pb.layout:
+        assert off % 256 == 0
+        v = getattr(pb, name)
+        assert v.dtype == getattr(b, name).dtype and tuple(v.shape) == tuple(getattr(b, name).shape)
+        assert torch.equal(v, getattr(b, name))
+        assert v.data_ptr() == pb.host.data_ptr() + off           # a view, not a copy
+    assert [l[0] for l in pb.layout] == list(FIELDS)
+    assert pb.payload_bytes() <= pb.nbytes
+    pb.x.zero_()
+    assert float(pb.host[:pb.layout[0][2]].view(torch.float32).abs().sum()) == 0.0
+    assert pb.signature() == PackedBatch.from_batch(synth.floorplans_batch(graphs=2, n=100, e=300, seed=9), pin=False).signature()

@@ -271,13 +271,15 @@ __device__ __forceinline__ float4 bwd_load_dy4(const BnBwdArgs& a, int64_t r, in
   return v;
 }
 
+// The per-thread chain (row index -> gathered gradient row) is latency-bound: four rows per thread, many CTAs.
+constexpr int BWD4_ROWS_PER_CTA = 64;
 // part: [nparts][2][C]; 256 threads = 16 row lanes x 16 column groups (64 columns), grid (ceil(C4 / 16), nparts)
 __global__ void __launch_bounds__(256) k_bn_bwd_partial4(BnBwdArgs a, int C4, float* __restrict__ part) {
   __shared__ float4 s1[256], s2[256];
   const int cg = blockIdx.x * 16 + (threadIdx.x & 15), rl = threadIdx.x >> 4;
   const int c = cg * 4;
-  const int64_t r0 = (int64_t)blockIdx.y * ST_ROWS_PER_CTA;
-  const int64_t r1 = min(a.M, r0 + ST_ROWS_PER_CTA);
+  const int64_t r0 = (int64_t)blockIdx.y * BWD4_ROWS_PER_CTA;
+  const int64_t r1 = min(a.M, r0 + BWD4_ROWS_PER_CTA);
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = p;
   if (cg < C4) {
     const float4 sc = __ldg(reinterpret_cast<const float4*>(a.stat + c)), sh = __ldg(reinterpret_cast<const float4*>(a.stat + a.C + c));
@@ -353,12 +355,15 @@ int bn_bwd_finalize(const float* part, int nparts, int64_t M, int C, const float
 }
 
 int bn_backward(const BnBwdArgs& a, Arena& ws, cudaStream_t st) {
-  const int nparts = (int)cdiv(a.M > 0 ? a.M : 1, ST_ROWS_PER_CTA);
-  float* part = ws.take((int64_t)nparts * 2 * a.C);
+  // (the workspace is sized for the finer of the two partitions so that the dry run needs no pointers)
+  const int nparts_max = (int)cdiv(a.M > 0 ? a.M : 1, BWD4_ROWS_PER_CTA);
+  float* part = ws.take((int64_t)nparts_max * 2 * a.C);
   float* bstat = ws.take(2 * a.C);
   if (ws.dry()) return YOLAT_OK;
   if (ws.overflow) return YOLAT_ERR_WORKSPACE;
-  const bool vec = bn_bwd_vec_ok(a) && ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(bstat)) & 15u) == 0;
+  const bool vec = bn_bwd_vec_ok(a) && nparts_max <= 65535 &&
+                   ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(bstat)) & 15u) == 0;
+  const int nparts = vec ? nparts_max : (int)cdiv(a.M > 0 ? a.M : 1, ST_ROWS_PER_CTA);
   if (vec) {
     k_bn_bwd_partial4<<<dim3((unsigned)cdiv(a.C / 4, 16), nparts), 256, 0, st>>>(a, a.C / 4, part);
   } else {

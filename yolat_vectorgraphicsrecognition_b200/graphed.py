@@ -8,6 +8,10 @@ sync-free, so the whole step can be captured once per batch *shape* and replayed
     loss = step(batch)        # batch: CPU (pinned) or CUDA tensors, like train.py:270-283
     optimizer.step()          # p.grad tensors are static across replays
 
+With a `batch.PackedBatch` (one pinned buffer) the inputs reach the device as ONE copy, and
+`step.prefetch(next_batch)` stages the next batch on a copy stream into a second input set while the current
+step runs (what a prefetching data loader does), so the host->device traffic leaves the critical path.
+
 A batch with a new shape signature (N, E, B) is captured on first use (3 eager warm-up steps, then the
 capture); graphs are kept per signature, so the padded / bucketed batches of a data loader re-use them.
 BatchNorm running statistics and `num_batches_tracked` are updated by the kernels themselves, so replay
@@ -16,6 +20,8 @@ keeps the reference's training semantics (cad_recognition/train.py:263-286).
 from types import SimpleNamespace
 
 import torch
+
+from .batch import PackedBatch
 
 _FIELDS = ('x', 'bbox_idx', 'edge', 'bbox', 'e_attr', 'labels')
 
@@ -31,9 +37,14 @@ class GraphedStep(object):
         if self.device.type != 'cuda':
             raise RuntimeError('GraphedStep needs the model on a CUDA device (no CPU path)')
         self._graphs = {}
+        self._copy_stream = None
+        self._staged = {}          # id(batch) -> entry whose inputs are in flight on the copy stream
+        self._next_slot = 0
 
     @staticmethod
     def signature(batch):
+        if isinstance(batch, PackedBatch):
+            return batch.signature()
         return tuple((f, tuple(getattr(batch, f).shape), getattr(batch, f).dtype) for f in _FIELDS)
 
     def _eager(self, static):
@@ -44,10 +55,24 @@ class GraphedStep(object):
             self.extra(loss)
         return loss, out[0]
 
+    @staticmethod
+    def _stage(entry, batch):
+        """Enqueue the host->device copies of `batch` into the entry's static inputs on the current stream:
+        one copy for a PackedBatch, one per field otherwise."""
+        if entry.buf is not None:
+            entry.buf.copy_(batch.host, non_blocking=True)
+        else:
+            for f in _FIELDS:
+                getattr(entry.static, f).copy_(getattr(batch, f), non_blocking=True)
+
     def _capture(self, batch):
-        static = SimpleNamespace(**{f: torch.empty_like(getattr(batch, f), device=self.device) for f in _FIELDS})
-        for f in _FIELDS:
-            getattr(static, f).copy_(getattr(batch, f), non_blocking=True)
+        if isinstance(batch, PackedBatch):
+            buf, static = batch.device_twin(self.device)
+        else:
+            buf = None
+            static = SimpleNamespace(**{f: torch.empty_like(getattr(batch, f), device=self.device) for f in _FIELDS})
+        entry = SimpleNamespace(buf=buf, static=static, ready=None, done=torch.cuda.Event())
+        self._stage(entry, batch)
         # warm up on a side stream: lazy initialisation (cudaFuncSetAttribute, workspace growth, cuda context
         # pieces) must happen outside the capture; gradients are created here and stay the same tensors
         side = torch.cuda.Stream(device=self.device)
@@ -65,27 +90,65 @@ class GraphedStep(object):
             p.grad = None
         with torch.cuda.graph(graph):
             loss, logits = self._eager(static)
-        entry = SimpleNamespace(graph=graph, static=static, loss=loss, logits=logits,
-                                grads=[p.grad for p in self.params])
+        entry.graph, entry.loss, entry.logits = graph, loss, logits
+        entry.grads = [p.grad for p in self.params]
         return entry
 
-    def __call__(self, batch):
-        sig = self.signature(batch)
-        entry = self._graphs.get(sig)
-        fresh = entry is None
-        if fresh:
+    def _entry(self, batch, slot):
+        """The captured graph (and its static inputs) for this batch shape; `slot` selects one of two input sets
+        so that the next batch can be staged while the current one is still being read."""
+        key = (self.signature(batch), slot)
+        entry = self._graphs.get(key)
+        if entry is None:
             state = {k: v.clone() for k, v in self.model.state_dict().items() if 'running_' in k or 'num_batches' in k}
+            grads = [p.grad for p in self.params]      # a capture (e.g. from prefetch) must not disturb the caller's grads
             entry = self._capture(batch)
-            self._graphs[sig] = entry
+            for p, g in zip(self.params, grads):
+                p.grad = g
+            self._graphs[key] = entry
             with torch.no_grad():     # undo the BN-buffer updates of the warm-up steps (capture itself runs nothing)
                 sd = self.model.state_dict()
                 for k, v in state.items():
                     sd[k].copy_(v)
+            entry.fresh = True
+        return entry
+
+    def prefetch(self, batch):
+        """Stage `batch` (host tensors, ideally a pinned PackedBatch) for the NEXT call on a copy stream, into the
+        input set the step in flight is not using: its host->device copy overlaps the current step's kernels."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        slot = self._next_slot
+        self._next_slot ^= 1
+        entry = self._entry(batch, slot)
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(entry, 'fresh', False):
+            entry.fresh = False                   # the capture just staged this very batch on the current stream
+            entry.ready = torch.cuda.Event()
+            entry.ready.record(cur)
         else:
-            for f in _FIELDS:
-                getattr(entry.static, f).copy_(getattr(batch, f), non_blocking=True)
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(entry.done)      # the last replay that read this input set has finished
+                self._stage(entry, batch)
+                entry.ready = torch.cuda.Event()
+                entry.ready.record(self._copy_stream)
+        self._staged[id(batch)] = entry
+        return entry
+
+    def __call__(self, batch):
+        cur = torch.cuda.current_stream(self.device)
+        entry = self._staged.pop(id(batch), None)
+        if entry is not None:
+            cur.wait_event(entry.ready)
+        else:
+            entry = self._entry(batch, 0)
+            if getattr(entry, 'fresh', False):
+                entry.fresh = False
+            else:
+                self._stage(entry, batch)
         for p, g in zip(self.params, entry.grads):
             p.grad = g
         entry.graph.replay()
+        entry.done.record(cur)
         self.last_logits = entry.logits
         return entry.loss
