@@ -205,6 +205,19 @@ int yolat_softmax_xent_fwd(const float* logits, int64_t ldl, int64_t B, int ncls
 int yolat_softmax_xent_bwd(const float* prob, int64_t B, int ncls, const int64_t* labels, const float* g_loss,
                            float* dlogits, int64_t ldd, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-tensor Adam (replaces torch.optim.Adam(...).step(), cad_recognition/train.py:212,284: one L2-regularised
+ * Adam update of every parameter tensor, ~100 eager launches per step in the reference).
+ *   table: n_chunks x 4 device addresses (param, grad, exp_avg, exp_avg_sq of the chunk's first element),
+ *   count: elements of each chunk (<= yolat_adam_chunk()),
+ *   state: 3 doubles on the device: [0] step count t (advanced by the call), [1] lr / (1 - beta1^t),
+ *          [2] 1 / sqrt(1 - beta2^t)  -- device-resident, so the call can be captured in a CUDA graph.
+ *   grad <- grad * grad_scale + weight_decay * param before the moment updates (torch semantics, not AdamW).
+ * ---------------------------------------------------------------------------------------------- */
+int yolat_adam_chunk(void);
+int yolat_adam_step(const uint64_t* table, const int32_t* count, int64_t n_chunks, double* state, double lr, double beta1,
+                    double beta2, double eps, double weight_decay, double grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,9 @@ _SIGS = {
                                     vp, vp, vp, vp, vp, vp, i64, vp]),
     'yolat_softmax_xent_fwd': (C.c_int, [vp, i64, i64, i32, vp, vp, vp, vp, i64, vp]),
     'yolat_softmax_xent_bwd': (C.c_int, [vp, i64, i32, vp, vp, vp, i64, vp]),
+    'yolat_adam_chunk': (C.c_int, []),
+    'yolat_adam_step': (C.c_int, [vp, vp, i64, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                  C.c_double, vp]),
 }
 
 _lib = None
