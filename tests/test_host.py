@@ -115,3 +115,71 @@ def test_packed_batch_layout_roundtrip():
     pb.x.zero_()
     assert float(pb.host[:pb.layout[0][2]].view(torch.float32).abs().sum()) == 0.0
     assert pb.signature() == PackedBatch.from_batch(synth.floorplans_batch(graphs=2, n=100, e=300, seed=9), pin=False).signature()
+
+
+def _proposal_forest(seed, n_images=2):
+    """Synthetic batch with the idxTree structure SparseCADGCN.predict walks (graph_dict3.py:750-768): per image a few
+    root proposals, each owning a contiguous node / edge range and a bbox row, with children owning sub-ranges."""
+    import torch
+    from types import SimpleNamespace
+    g = torch.Generator().manual_seed(seed)
+    roots, slices = [], {'roots': [0], 'pos': [], 'edge': [], 'bbox': []}
+    xs, edges, attrs, bidx, n_bbox = [], [], [], [], 0
+    pos_off = edge_off = 0
+    for img in range(n_images):
+        slices['pos'].append(pos_off); slices['edge'].append(edge_off); slices['bbox'].append(n_bbox)
+        p = e = b = 0
+        for r in range(3 + img):
+            n_r = int(torch.randint(4, 9, (1,), generator=g))
+            kids, first_p, first_e = [], p, e
+            for c in range(int(torch.randint(0, 3, (1,), generator=g))):
+                n_c = int(torch.randint(2, 5, (1,), generator=g))
+                e_c = n_c + 1
+                kids.append(SimpleNamespace(value={'idx_pos': (p, p + n_c), 'idx_edge': (e, e + e_c), 'idx_bbox': b}, children=[]))
+                for _ in range(e_c):
+                    edges.append([pos_off + p + int(torch.randint(0, n_c, (1,), generator=g)),
+                                  pos_off + p + int(torch.randint(0, n_c, (1,), generator=g))])
+                bidx += [n_bbox + b] * n_c
+                p += n_c; e += e_c; b += 1
+            # the root's own nodes follow its children's and its edges stay inside [first_p, p + n_r)
+            for _ in range(n_r):
+                edges.append([pos_off + first_p + int(torch.randint(0, p + n_r - first_p, (1,), generator=g)),
+                              pos_off + first_p + int(torch.randint(0, p + n_r - first_p, (1,), generator=g))])
+            bidx += [n_bbox + b] * n_r
+            roots.append(SimpleNamespace(value={'idx_pos': (first_p, p + n_r), 'idx_edge': (first_e, e + n_r), 'idx_bbox': b},
+                                         children=kids))
+            p += n_r; e += n_r; b += 1
+        pos_off += p; edge_off += e; n_bbox += b
+        slices['roots'].append(len(roots))
+    N, E = pos_off, edge_off
+    data = SimpleNamespace(x=torch.randn(N, 5, generator=g), pos=torch.rand(N, 2, generator=g),
+                           bbox_idx=torch.tensor(bidx), edge=torch.tensor(edges, dtype=torch.long),
+                           e_attr=torch.randn(E, 4, generator=g), bbox=torch.rand(n_bbox, 4, generator=g),
+                           stat_feats=torch.rand(n_bbox, 13, generator=g), roots=roots)
+    assert data.edge.shape[0] == E and len(bidx) == N
+    return data, slices
+
+
+def test_predict_slicing_matches_the_reference_loops():
+    """The vectorised `_ranges` / `_build_data` of the host mirror against the plain-Python restatement of the
+    reference's loops (oracle/predict_slicing.py; architecture3cc_rpn_gp_iter2.py:153-234), on roots and on children."""
+    import torch
+    from oracle import predict_slicing as P
+    from yolat_vectorgraphicsrecognition_b200.architecture3cc_rpn_gp_iter2 import SparseCADGCN
+    for seed in (0, 1, 2):
+        data, slices = _proposal_forest(seed)
+        root_nodes, child_nodes = [], []
+        for i in range(len(slices['roots']) - 1):
+            for root in data.roots[slices['roots'][i]:slices['roots'][i + 1]]:
+                root_nodes.append((root, i))
+                child_nodes += [(c, i) for c in root.children]
+        for nodes in (root_nodes, child_nodes):
+            if not nodes:
+                continue
+            sp_ref, se_ref, sb_ref = P.ranges(nodes, slices)
+            ref = P.build_data(data, sp_ref, se_ref, sb_ref)
+            sp, se, sb = SparseCADGCN._ranges(nodes, slices, None)
+            assert list(sp) == sp_ref and list(se) == se_ref and list(sb) == sb_ref
+            got = SparseCADGCN._build_data(data, sp, se, sb)
+            for k in ('x', 'pos', 'bbox_idx', 'edge', 'e_attr', 'bbox', 'stat_feats'):
+                assert torch.equal(getattr(got, k), getattr(ref, k)), (seed, k)
