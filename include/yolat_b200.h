@@ -218,6 +218,22 @@ int yolat_adam_chunk(void);
 int yolat_adam_step(const uint64_t* table, const int32_t* count, int64_t n_chunks, double* state, double lr, double beta1,
                     double beta2, double eps, double weight_decay, double grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Proposal slicing of SparseCADGCN.predict on the device (architecture3cc_rpn_gp_iter2.py:153-234: python range
+ * lists, the old->new node dict, the per-edge re-indexing loop, the per-node bbox_idx renumbering loop).
+ *   yolat_expand_ranges: out[t] = start[k] + (t - prefix[k]) for the range k holding t; prefix = exclusive prefix
+ *                        sums of the K range lengths (prefix[0] = 0), total = their sum.  All device int64.
+ *   yolat_slice_graph:   pos_idx [Np] / edge_idx [Ep] = expanded node / edge selections; edge [E_all,2] int64;
+ *                        edge_out[e] = (new index of edge[edge_idx[e]][0], ...[1]) (-1 if the endpoint is not selected),
+ *                        bbox_idx_out[t] = number of changes of bbox_idx[pos_idx[.]] in (0, t]  (dense renumbering);
+ *                        ws: yolat_slice_graph_ints(N_all, Np) int32.
+ * ---------------------------------------------------------------------------------------------- */
+int yolat_expand_ranges(const int64_t* start, const int64_t* prefix, int64_t K, int64_t total, int64_t* out, void* stream);
+int64_t yolat_slice_graph_ints(int64_t N_all, int64_t Np);
+int yolat_slice_graph(const int64_t* pos_idx, int64_t Np, const int64_t* edge_idx, int64_t Ep, const int64_t* edge,
+                      int64_t E_all, int64_t N_all, const int64_t* bbox_idx, int32_t* ws, int64_t* edge_out,
+                      int64_t* bbox_idx_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

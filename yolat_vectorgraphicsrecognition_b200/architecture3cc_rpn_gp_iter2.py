@@ -192,6 +192,58 @@ class SparseCADGCN(torch.nn.Module):
             nd.bbox_idx = old_bidx
         return nd
 
+    def _device_data(self, data):
+        """The batch on the model's device, moved once per predict() (the reference re-slices on the host and copies
+        every slice: :167-234, :107-115)."""
+        from types import SimpleNamespace
+        dev = self._device()
+        out = SimpleNamespace()
+        for k in ('x', 'pos', 'bbox_idx', 'edge', 'e_attr', 'bbox', 'stat_feats'):
+            v = getattr(data, k, None)
+            setattr(out, k, None if v is None else _dev(v, dev).contiguous())
+        return out
+
+    @staticmethod
+    def _build_data_device(dd, nodes, slices):
+        """`_ranges` + `_build_data` on the device (csrc/slicing.cu): the K (start, length) pairs of the selected
+        proposals are the only host data; range expansion, the old->new renumbering of edge endpoints and the dense
+        bbox_idx renumbering are kernels, the row gathers are index_selects.  Returns (batch namespace, slice_bbox)."""
+        from types import SimpleNamespace
+        from . import _lib as L
+        lib = L.lib()
+        dev = dd.x.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        K = len(nodes)
+        tab = np.zeros((4, K + 1), dtype=np.int64)          # pos start | pos prefix | edge start | edge prefix
+        bbox = []
+        for k, (node, i) in enumerate(nodes):
+            v = node.value
+            tab[0, k] = v['idx_pos'][0] + int(slices['pos'][i])
+            tab[1, k + 1] = tab[1, k] + (v['idx_pos'][1] - v['idx_pos'][0])
+            tab[2, k] = v['idx_edge'][0] + int(slices['edge'][i])
+            tab[3, k + 1] = tab[3, k] + (v['idx_edge'][1] - v['idx_edge'][0])
+            bbox.append(int(v['idx_bbox'] + slices['bbox'][i]))
+        Np, Ep = int(tab[1, K]), int(tab[3, K])
+        t = torch.from_numpy(tab).to(dev)
+        sp = torch.empty(Np, dtype=torch.long, device=dev)
+        se = torch.empty(Ep, dtype=torch.long, device=dev)
+        L.check(lib.yolat_expand_ranges(t[0].data_ptr(), t[1].data_ptr(), K, Np, L.ptr(sp), st), 'yolat_expand_ranges')
+        L.check(lib.yolat_expand_ranges(t[2].data_ptr(), t[3].data_ptr(), K, Ep, L.ptr(se), st), 'yolat_expand_ranges')
+        N_all, E_all = dd.x.shape[0], dd.edge.shape[0]
+        ws = torch.empty(int(lib.yolat_slice_graph_ints(N_all, Np)), dtype=torch.int32, device=dev)
+        nd = SimpleNamespace()
+        nd.edge = torch.empty(Ep, 2, dtype=torch.long, device=dev)
+        nd.bbox_idx = torch.empty(Np, dtype=torch.long, device=dev)
+        L.check(lib.yolat_slice_graph(L.ptr(sp), Np, L.ptr(se), Ep, L.ptr(dd.edge), E_all, N_all, L.ptr(dd.bbox_idx),
+                                      L.ptr(ws), L.ptr(nd.edge), L.ptr(nd.bbox_idx), st), 'yolat_slice_graph')
+        sb = torch.as_tensor(bbox, dtype=torch.long, device=dev)
+        nd.x = dd.x.index_select(0, sp)
+        nd.pos = dd.pos.index_select(0, sp) if dd.pos is not None else None
+        nd.e_attr = dd.e_attr.index_select(0, se)
+        nd.bbox = dd.bbox.index_select(0, sb)
+        nd.stat_feats = dd.stat_feats.index_select(0, sb) if dd.stat_feats is not None else None
+        return nd, bbox
+
     def predict(self, data, slices):
         roots = data.roots
         slice_root = slices['roots']
@@ -200,8 +252,9 @@ class SparseCADGCN(torch.nn.Module):
             for root in roots[slice_root[i]:slice_root[i + 1]]:
                 root_nodes.append((root, i))
             slice_image_bbox_root.append(len(root_nodes))
-        sp, se, slice_bbox = self._ranges(root_nodes, slices, None)
-        pred_cls, pred_bbox = self.forward(self._build_data(data, sp, se, slice_bbox), slices)
+        dd = self._device_data(data)
+        nd, slice_bbox = self._build_data_device(dd, root_nodes, slices)
+        pred_cls, pred_bbox = self.forward(nd, slices)
 
         _, is_object = pred_cls.max(1)
         has_object = (is_object == self.n_classes - 1).cpu()
@@ -216,13 +269,14 @@ class SparseCADGCN(torch.nn.Module):
                         child_nodes.append((child, i))
                 count += 1
             slice_image_bbox_child.append(len(child_nodes))
-        sp, se, slice_bbox = self._ranges(child_nodes, slices, None)
+        n_child_pos = sum(c.value['idx_pos'][1] - c.value['idx_pos'][0] for c, _ in child_nodes)
 
-        if len(sp) == 0:
+        if n_child_pos == 0:                                   # `len(slice_pos) == 0` (:299)
             slice_image_bbox = slice_image_bbox_root
             slice_bbox = slice_bbox_root
         else:
-            pred_cls2, pred_bbox2 = self.forward(self._build_data(data, sp, se, slice_bbox), slices)
+            nd2, slice_bbox = self._build_data_device(dd, child_nodes, slices)
+            pred_cls2, pred_bbox2 = self.forward(nd2, slices)
 
             def interleaf_pc(slice_p, slice_c, out_p, out_c):
                 out, s = [], [0]
