@@ -63,7 +63,15 @@ constexpr uint32_t OFF_BN2 = OFF_CARRY + 2 * C * 4;
 constexpr uint32_t SMEM_BYTES = OFF_BN2 + 2 * C * 4 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
-enum { F_TAPE = 1, F_STATS = 2, F_AGG = 4, F_Z1 = 8 };   // F_Z1: pass A -- BatchNorm-1 statistics of z1 only (no MMA)
+enum { F_TAPE = 1, F_STATS = 2, F_AGG = 4, F_Z1 = 8 };
+
+// -DYOLAT_EF_TRACE: per-tile clock64 timestamps of the roles of one CTA (tools/ef_trace.py); never in the product build.
+#ifdef YOLAT_EF_TRACE
+__device__ long long g_ef_trace[128 * 16];
+#define EF_TRACE(tile, ev) do { if (blockIdx.x == 74 && (tile) < 128) g_ef_trace[(tile) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define EF_TRACE(tile, ev) do { } while (0)
+#endif   // F_Z1: pass A -- BatchNorm-1 statistics of z1 only (no MMA)
 
 struct Params {
   const int32_t* rowptr; const int32_t* src; const int32_t* dst; const int32_t* eid; const float* deg_inv;
@@ -102,9 +110,15 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
 // tiles of 128 slots through a pipeline of mbarrier-connected roles (no CTA-wide barrier inside the loop):
 //     ring fill (idx, attr; PF - 4 tiles ahead)  ->  gather warps  --a1 stage (smem, UMMA layout, 2 stages)-->
 //     tcgen05.mma  --z2 accumulator (TMEM, 2 x 64 columns)-->  epilogue warps (statistics | segmented mean | tape)
-template <int FLAGS, int E_WARPS, int G_WARPS, bool MMA_G>
-__global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(const Params p) {
-  constexpr int E_THREADS = E_WARPS * 32, G_THREADS = G_WARPS * 32, THREADS = E_THREADS + G_THREADS;
+// MMA_MODE: who issues the tcgen05.mma of a tile (the issue loop blocks for the ~1.2k cycles the tensor core needs for a
+// tile's 24 MMAs -- their operand reads are shared-memory bound -- so whoever issues cannot do anything else meanwhile):
+//   0 epilogue warp 0, 1 a rotating gather warp, 2 a dedicated control warp (a fourth warp group of which one warp
+//   works; register budgets are rebalanced with setmaxnreg: control 96 -> 24, gather 96 -> 128 per thread; the pool only
+//   holds what the control group released, so the sum after must not exceed 20 warps x 96).
+template <int FLAGS, int E_WARPS, int G_WARPS, int MMA_MODE>
+__global__ void __launch_bounds__((E_WARPS + G_WARPS + (MMA_MODE == 2 ? 4 : 0)) * 32, 1) k_edge_fused(const Params p) {
+  constexpr bool MMA_G = MMA_MODE == 1, MMA_E = MMA_MODE == 0, CTRL = MMA_MODE == 2;
+  constexpr int E_THREADS = E_WARPS * 32, G_THREADS = G_WARPS * 32, THREADS = E_THREADS + G_THREADS + (CTRL ? 128 : 0);
   constexpr int SPT = TILE * 16 / G_THREADS;              // slots per gather thread and tile (16 threads per slot)
   constexpr int NSLG = TILE / SPT;                        // slot groups: slot = i * NSLG + sl
   constexpr int NSG = E_THREADS / 16;                     // F_STATS: slot groups of the column sums
@@ -187,16 +201,17 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
   const int ntiles = (int)((s_end - s_begin + TILE - 1) / TILE);
 
   // ---- tcgen05.mma issue: z2 = a1 W2^T, 3xTF32, accumulator (tile & 1) in TMEM.  Called by one whole warp, one
-  //      elected lane issues.  MMA_G: gather warp t % G_WARPS, after its own arrival, waits for the other gather warps
-  //      (they finish within a few hundred cycles of each other), so the product of tile t starts the moment its a1
-  //      stage is complete; the duty rotates over the warps.  !MMA_G: epilogue warp 0, one tile ahead of its drain.
-  //      Either way the product of tile t overlaps the epilogue of tile t-1 and the gathers of tile t+1.
+  //      elected lane issues the whole tile and blocks until the tensor core has taken all 24 MMAs (~1.3k cycles).
+  //      Used by epilogue warp 0 (MMA_MODE 0, one tile ahead of its drain), by the control warp (MODE 2) and for the
+  //      last tile of MODE 1; otherwise MODE 1 issues piece-wise (issue_kstep below).
   auto issue_mma = [&](int t) {
     constexpr uint32_t IDESC = make_idesc(TILE, C, 0, 0);
     const int s = t & 1;
     const uint32_t a_u32 = sm_u32 + (uint32_t)s * A_STAGE, w_u32 = sm_u32 + OFF_W;
     mbar_wait_park(smem_u32(&bar_a_full[s]), (uint32_t)((t >> 1) & 1));
+    if (lane == 0) EF_TRACE(t, 11);
     if (t >= 2) mbar_wait_park(smem_u32(&bar_acc_empty[s]), (uint32_t)(((t >> 1) - 1) & 1));
+    if (lane == 0) EF_TRACE(t, 12);
     tc_fence_after();
     const uint32_t d = tmem_d + (uint32_t)(s * C);
     if (elect_one_sync()) {
@@ -221,6 +236,32 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
     __syncwarp();
   };
 
+  // One k-step (8 of the 64 reduction indices: three tcgen05.mma) of tile t -- the piece-wise form of issue_mma used by the
+  // gather warp on MMA duty: issued between its slots of the next tile, the tensor core's queue never fills and the
+  // issuing lane never blocks (a whole tile issued at once blocks for the ~1.3k cycles the MMAs take).
+  auto issue_kstep = [&](int t, int k) {
+    constexpr uint32_t IDESC = make_idesc(TILE, C, 0, 0);
+    const int s = t & 1, kb = k >> 2, ks = k & 3;
+    const uint32_t a_u32 = sm_u32 + (uint32_t)s * A_STAGE, w_u32 = sm_u32 + OFF_W;
+    const uint32_t d = tmem_d + (uint32_t)(s * C);
+    if (elect_one_sync()) {
+      const uint32_t ao = (uint32_t)kb * A_KB + (uint32_t)ks * 32u;
+      const uint32_t bo = (uint32_t)kb * W_KB + (uint32_t)ks * 32u;
+      const uint64_t a_hi = make_desc(a_u32 + ao, 16, 1024, LAYOUT_SW128);
+      const uint64_t a_lo = make_desc(a_u32 + A_HI + ao, 16, 1024, LAYOUT_SW128);
+      const uint64_t b_hi = make_desc(w_u32 + bo, 16, 1024, LAYOUT_SW128);
+      const uint64_t b_lo = make_desc(w_u32 + W_HI + bo, 16, 1024, LAYOUT_SW128);
+      umma_tf32(d, a_lo, b_hi, IDESC, k > 0 ? 1u : 0u);
+      umma_tf32(d, a_hi, b_lo, IDESC, 1u);
+      umma_tf32(d, a_hi, b_hi, IDESC, 1u);
+      if (k == 7) {
+        umma_commit(smem_u32(&bar_acc_full[s]));    // z2 of this tile is complete ...
+        umma_commit(smem_u32(&bar_a_empty[s]));     // ... and its a1 stage may be refilled
+      }
+    }
+    __syncwarp();
+  };
+
   if (warp < E_WARPS) {
     // =========================== epilogue warps ==========================================================
     const int q = warp & 3, slot = q * 32 + lane, et = tid;
@@ -240,7 +281,7 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
       bulk_g2s(dst, p.rec_idx + s0, bytes, bar);
       bulk_g2s(dst + TILE * 16, p.rec_attr + s0, bytes, bar);
     };
-    const bool producer = (tid == 0);
+    const bool producer = !CTRL && (tid == 0);
     if (producer) {
       for (int j = 0; j < PF; ++j) fill(j);
     }
@@ -288,7 +329,7 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
       for (int q2 = 0; q2 < NPF; ++q2) row_meta(R_prev + rl + q2 * RIF, nb[q2], ne_[q2], ndi[q2], nbase[q2], true);
     }
 
-    if (!MMA_G && warp == 0 && ntiles > 0) issue_mma(0);
+    if (MMA_E && warp == 0 && ntiles > 0) issue_mma(0);
     constexpr bool SH_REG = FOLD && E_WARPS == 8;    // one column half per thread: its BN2 shifts live in registers
     float shr[SH_REG ? 32 : 1];
     if (SH_REG) {
@@ -297,15 +338,36 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
     }
     for (int t = 0; t < ntiles; ++t) {
       if (producer) fill(t + PF);                    // never blocks in practice: the gather finished tile t - 1 long ago
-      if (!MMA_G && warp == 0 && t + 1 < ntiles) issue_mma(t + 1);
+      if (MMA_E && warp == 0 && t + 1 < ntiles) issue_mma(t + 1);
       const int a = t & 1;
       const int64_t s0 = s_begin + (int64_t)t * TILE;
       const int nvalid = (int)min((int64_t)TILE, s_end - s0);
       float wgt = 1.f;
       if ((FLAGS & F_AGG) && p.ew && slot < nvalid) wgt = __ldg(p.ew + __ldg(p.eid + s0 + slot));
+      // F_AGG: the row bookkeeping of the next tile is requested here, a whole drain ahead of its first use (the
+      // boundary row R_next of tile t + 1 is needed when this iteration ends: requested after the row sums it used to
+      // cost a global-memory round trip per tile).  The current tile's copy moves to c* first.
+      int cb[NPF], ce[NPF], R_next = r_end;
+      float cdi[NPF];
+      float4 cbs[NPF][CPT];
+      if (FLAGS & F_AGG) {
+#pragma unroll
+        for (int q2 = 0; q2 < NPF; ++q2) {
+          cb[q2] = nb[q2]; ce[q2] = ne_[q2]; cdi[q2] = ndi[q2];
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) cbs[q2][k] = nbase[q2][k];
+        }
+        if (t + 1 < ntiles) R_next = tile_rcur(t + 1);
+#pragma unroll
+        for (int q2 = 0; q2 < NPF; ++q2)
+          row_meta(R_cur + rl + q2 * RIF, nb[q2], ne_[q2], ndi[q2], nbase[q2], t + 1 < ntiles);
+      }
+      if (tid == 0) EF_TRACE(t, 0);
       mbar_wait_park(smem_u32(&bar_acc_full[a]), (uint32_t)((t >> 1) & 1));
       tc_fence_after();
+      if (tid == 0) EF_TRACE(t, 1);
       named_bar_sync(1, E_THREADS);                 // the readers of the previous tile's staging rows have finished
+      if (tid == 0) EF_TRACE(t, 2);
       for (int h = h_begin; h < h_end; ++h) {
         float v[32];
         tmem_ld32(tmem_d + (uint32_t)(a * C) + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32), v);
@@ -356,7 +418,9 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
           }
         }
       }
+      if (tid == 0) EF_TRACE(t, 3);
       named_bar_sync(1, E_THREADS);
+      if (tid == 0) EF_TRACE(t, 4);
       if (FLAGS & F_STATS) {
         // column sums of the staging tile: this thread owns 4 channels of TILE / NSG slots
 #pragma unroll 4
@@ -377,19 +441,6 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
         const bool last = s1 >= s_end;
         const float* cin = carry + (t & 1) * C;
         float* cout = carry + ((t + 1) & 1) * C;
-        int cb[NPF], ce[NPF];
-        float cdi[NPF];
-        float4 cbs[NPF][CPT];
-#pragma unroll
-        for (int q2 = 0; q2 < NPF; ++q2) {
-          cb[q2] = nb[q2]; ce[q2] = ne_[q2]; cdi[q2] = ndi[q2];
-#pragma unroll
-          for (int k = 0; k < CPT; ++k) cbs[q2][k] = nbase[q2][k];
-        }
-        const int R_next = (t + 1 < ntiles) ? tile_rcur(t + 1) : r_end;      // used one tile later
-#pragma unroll
-        for (int q2 = 0; q2 < NPF; ++q2)                                     // the first rows of the next tile
-          row_meta(R_cur + rl + q2 * RIF, nb[q2], ne_[q2], ndi[q2], nbase[q2], t + 1 < ntiles);
         auto reduce_row = [&](int r, int b, int e, float di, const float4 (&bs)[CPT]) {
           if (r > R_cur || (r == R_cur && last)) return;
           const bool done = r < R_cur;
@@ -440,6 +491,7 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
         R_prev = R_cur;
         R_cur = R_next;
       }
+      if (tid == 0) EF_TRACE(t, 5);
     }
     if ((FLAGS & F_AGG) && ntiles == 0) {           // a range of rows without a single slot: out = base
       for (int r = r_begin + rl; r < r_end; r += RIF) {
@@ -470,8 +522,34 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
       }
     }
     }   // !F_Z1
+  } else if (CTRL && warp >= E_WARPS + G_WARPS) {
+    // =========================== control warp group: TMA producer + MMA issuer (first warp only) =========
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == E_WARPS + G_WARPS) {
+      auto fillc = [&](int j) {
+        if (j >= ntiles) return;
+        const int st = j % RING;
+        if (j >= RING) mbar_wait_park(smem_u32(&bar_ring_empty[st]), (uint32_t)(((j / RING) - 1) & 1));
+        const int64_t s0 = s_begin + (int64_t)j * TILE;
+        const uint32_t bytes = (uint32_t)min((int64_t)TILE, s_end - s0) * 16u;
+        const uint32_t bar = smem_u32(&bar_ring_full[st]);
+        const uint32_t dst = smem_u32(ring + st * RING_BYTES);
+        mbar_expect_tx(bar, 2u * bytes);
+        bulk_g2s(dst, p.rec_idx + s0, bytes, bar);
+        bulk_g2s(dst + TILE * 16, p.rec_attr + s0, bytes, bar);
+      };
+      if (lane == 0) {
+        for (int j = 0; j < PF; ++j) fillc(j);
+      }
+      for (int t = 0; t < ntiles; ++t) {
+        if (lane == 0) fillc(t + PF);
+        __syncwarp();
+        if (!(FLAGS & F_Z1)) issue_mma(t);
+      }
+    }
   } else {
     // =========================== gather warps ============================================================
+    if (CTRL) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     // Thread (gc, sl): channels 4gc .. 4gc+3 of slots i * NSLG + sl (i < SPT) of every tile -- the two half-warps work
     // on adjacent slots, so their record reads share a wavefront and their a1 rows share an 8-row swizzle atom.  The
     // P / Q rows of tile t+1 are requested slot by slot while tile t is being computed ("rolling" register prefetch:
@@ -524,10 +602,23 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
       const int nvalid = (int)min((int64_t)TILE, s_end - s0);
       const int st_cur = it % RING, st_next = (it + 1) % RING;
       const bool have_next = it + 1 < ntiles;
+      if (g == 0) EF_TRACE(it, 6);
       if (have_next) mbar_wait_park(smem_u32(&bar_ring_full[st_next]), (uint32_t)(((it + 1) / RING) & 1));
+      if (g == 0) EF_TRACE(it, 7);
       if (!(FLAGS & F_Z1) && it >= 2) mbar_wait_park(smem_u32(&bar_a_empty[s]), (uint32_t)(((it >> 1) - 1) & 1));
+      if (g == 0) EF_TRACE(it, 8);
       uint8_t* a_tile = sm + (uint32_t)s * A_STAGE;
       const float4* attr_s = reinterpret_cast<const float4*>(ring + st_cur * RING_BYTES + TILE * 16);
+      // MMA duty (MMA_G): gather warp (it - 1) % G_WARPS issues the product of tile it - 1 while it gathers tile it, one
+      // k-step after each of its slots.  Every warp arrived for tile it - 1 before starting this one, so the waits below
+      // are short; the duty rotates, so no warp falls behind the others.
+      const bool duty = MMA_G && !(FLAGS & F_Z1) && it >= 1 && gw == (it - 1) % G_WARPS;
+      if (duty) {
+        const int tp = it - 1;
+        mbar_wait_park(smem_u32(&bar_a_full[tp & 1]), (uint32_t)((tp >> 1) & 1));
+        if (tp >= 2) mbar_wait_park(smem_u32(&bar_acc_empty[tp & 1]), (uint32_t)(((tp >> 1) - 1) & 1));
+        tc_fence_after();
+      }
       if (it + PFL2 < ntiles) {
         // L2 prefetch of the P / Q rows of tile it + PFL2 (its records are already in the ring): the register loads
         // above run only one tile ahead of their use, which hides an L2 hit but not a DRAM miss.  Four 128-byte lines
@@ -568,6 +659,10 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
         float2 a0 = ffma2(v0, sc1[0], sh1[0]), a1 = ffma2(v1, sc1[1], sh1[1]);
         a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f); a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f);
         store_split_trunc(a_tile, a_tile + A_HI, off0 + (uint32_t)(i * (NSLG / 8)) * 1024u, a0, a1);   // a1 >= 0, finite
+        if (duty) {
+#pragma unroll
+          for (int k = i * (8 / SPT); k < (i + 1) * (8 / SPT); ++k) issue_kstep(it - 1, k);
+        }
       }
       if (FLAGS & F_Z1) {
         warp_arrive(smem_u32(&bar_ring_empty[st_cur]), lane);
@@ -579,10 +674,11 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS) * 32, 1) k_edge_fused(cons
         mbar_arrive(smem_u32(&bar_a_full[s]));
         mbar_arrive(smem_u32(&bar_ring_empty[st_cur]));   // idx (read one tile ago) and attr of this tile are consumed
       }
-      if (MMA_G && gw == it % G_WARPS) {
-        __syncwarp();
-        issue_mma(it);
-      }
+      if (g == 0) EF_TRACE(it, 9);
+    }
+    if (MMA_G && !(FLAGS & F_Z1) && ntiles > 0 && gw == (ntiles - 1) % G_WARPS) {     // the last tile: nothing left to overlap
+      __syncwarp();
+      issue_mma(ntiles - 1);
     }
     if (FLAGS & F_Z1) {                                   // combine the slot groups; part = [sum | sum of squares]
       float* red = reinterpret_cast<float*>(sm);          // [2][NSLG][C], the a1 ring is unused in this pass
@@ -627,7 +723,7 @@ static int roles() {
   return v;
 }
 
-template <int FLAGS, int EW, int GW, bool MG>
+template <int FLAGS, int EW, int GW, int MG>
 static cudaError_t launch_cfg(const Params& p, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
@@ -635,7 +731,7 @@ static cudaError_t launch_cfg(const Params& p, int grid, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  k_edge_fused<FLAGS, EW, GW, MG><<<grid, (EW + GW) * 32, SMEM_BYTES, st>>>(p);
+  k_edge_fused<FLAGS, EW, GW, MG><<<grid, (EW + GW + (MG == 2 ? 4 : 0)) * 32, SMEM_BYTES, st>>>(p);
   return cudaSuccess;
 }
 
@@ -649,10 +745,12 @@ static int mma_by_gather(int flags) {
 
 template <int FLAGS>
 static cudaError_t launch(const Params& p, int grid, cudaStream_t st) {
-  const bool mg = mma_by_gather(FLAGS) != 0;
+  const int mg = mma_by_gather(FLAGS);
   switch (roles()) {
-    case 1: return mg ? launch_cfg<FLAGS, 8, 8, true>(p, grid, st) : launch_cfg<FLAGS, 8, 8, false>(p, grid, st);
-    default: return mg ? launch_cfg<FLAGS, 4, 16, true>(p, grid, st) : launch_cfg<FLAGS, 4, 16, false>(p, grid, st);
+    case 1:
+      return mg == 2 ? launch_cfg<FLAGS, 8, 8, 2>(p, grid, st)
+                     : (mg == 1 ? launch_cfg<FLAGS, 8, 8, 1>(p, grid, st) : launch_cfg<FLAGS, 8, 8, 0>(p, grid, st));
+    default: return mg ? launch_cfg<FLAGS, 4, 16, 1>(p, grid, st) : launch_cfg<FLAGS, 4, 16, 0>(p, grid, st);
   }
 }
 
@@ -732,3 +830,9 @@ int edge_fused(const GraphView& g, int64_t N, int64_t E, int flags, const float*
 }
 
 }  // namespace yolat
+
+#ifdef YOLAT_EF_TRACE
+extern "C" int yolat_debug_ef_trace(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, yolat::ef::g_ef_trace, sizeof(long long) * 128 * 16);
+}
+#endif
