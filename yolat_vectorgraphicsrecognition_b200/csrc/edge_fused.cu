@@ -113,7 +113,7 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
 // MMA_MODE: who issues the tcgen05.mma of a tile (the issue loop blocks for the ~1.2k cycles the tensor core needs for a
 // tile's 24 MMAs -- their operand reads are shared-memory bound -- so whoever issues cannot do anything else meanwhile):
 //   0 epilogue warp 0, 1 a rotating gather warp, 2 a dedicated control warp (a fourth warp group of which one warp
-//   works; register budgets are rebalanced with setmaxnreg: control 96 -> 24, gather 96 -> 128 per thread; the pool only
+//   works; register budgets are rebalanced with setmaxnreg: control 96 -> 32, gather 96 -> 128 per thread; the pool only
 //   holds what the control group released, so the sum after must not exceed 20 warps x 96).
 template <int FLAGS, int E_WARPS, int G_WARPS, int MMA_MODE>
 __global__ void __launch_bounds__((E_WARPS + G_WARPS + (MMA_MODE == 2 ? 4 : 0)) * 32, 1) k_edge_fused(const Params p) {
@@ -124,7 +124,8 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS + (MMA_MODE == 2 ? 4 : 0)) 
   constexpr int NSG = E_THREADS / 16;                     // F_STATS: slot groups of the column sums
   constexpr int TPR = E_THREADS / 32;                     // F_AGG: threads per target row
   constexpr int RIF = 32;                                 // F_AGG: rows per sweep of the epilogue threads
-  constexpr int NPF = 2;                                  // F_AGG: sweeps whose row bookkeeping is prefetched a tile ahead
+  constexpr int NPF = CTRL ? 1 : 2;                       // F_AGG: sweeps whose row bookkeeping is prefetched a tile ahead
+                                                          // (one in control-warp mode: the epilogue has 96 registers there)
   constexpr int CPT = 16 / TPR;                           // F_AGG: 16-byte chunks per thread (chunk k at ch + 4 TPR k)
   static_assert(E_WARPS == 4 || E_WARPS == 8, "epilogue mapping");
   static_assert(SPT * G_THREADS == TILE * 16 && (SPT == 4 || SPT == 8), "gather mapping");
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS + (MMA_MODE == 2 ? 4 : 0)) 
     }
 
     if (MMA_E && warp == 0 && ntiles > 0) issue_mma(0);
-    constexpr bool SH_REG = FOLD && E_WARPS == 8;    // one column half per thread: its BN2 shifts live in registers
+    constexpr bool SH_REG = FOLD && E_WARPS == 8 && !CTRL;   // one column half per thread: its BN2 shifts live in registers
     float shr[SH_REG ? 32 : 1];
     if (SH_REG) {
 #pragma unroll
@@ -524,7 +525,7 @@ __global__ void __launch_bounds__((E_WARPS + G_WARPS + (MMA_MODE == 2 ? 4 : 0)) 
     }   // !F_Z1
   } else if (CTRL && warp >= E_WARPS + G_WARPS) {
     // =========================== control warp group: TMA producer + MMA issuer (first warp only) =========
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == E_WARPS + G_WARPS) {
       auto fillc = [&](int j) {
         if (j >= ntiles) return;
@@ -735,12 +736,15 @@ static cudaError_t launch_cfg(const Params& p, int grid, cudaStream_t st) {
   return cudaSuccess;
 }
 
-// Who issues the MMAs: the role that is not the bottleneck of the pass.  Measured at N = 320 000, E = 1 280 000 (8x8):
-// F_STATS 144 us (epilogue issues) vs 163 us (gather issues); F_AGG 237 us vs 187 us.  YOLAT_EF_MG = 0 / 1 forces one.
+// Who issues the MMAs (MMA_MODE of the kernel).  Measured at N = 320 000, E = 1 280 000 (8x8 warps):
+//   F_STATS  144 us (0: epilogue warp 0)   155 us (1: gather warps, piece-wise)   127 us (2: control warp)
+//   F_AGG    237 us                        180 us                                 169 us
+// Pass A has no MMAs and runs in mode 0.  YOLAT_EF_MG = 0 / 1 / 2 forces one mode for the two MMA passes.
 static int mma_by_gather(int flags) {
   static int v = -2;
   if (v == -2) { const char* e = getenv("YOLAT_EF_MG"); v = e ? atoi(e) : -1; }
-  return v >= 0 ? v : ((flags & F_AGG) ? 1 : 0);
+  if (flags & F_Z1) return 0;
+  return v >= 0 ? v : 2;
 }
 
 template <int FLAGS>
