@@ -3,34 +3,35 @@
 // Reference chain (gcn_lib/sparse/torch_vertex.py:324-337 + PyG propagate + torch_nn.py:58-68 + scatter-mean):
 //     x_i, x_j = index_select ; f = cat(x_i, x_j - x_i, attr) ; z1 = Lin1(f) ; a1 = relu(bn1(z1)) ;
 //     z2 = Lin2(a1) ; m = relu(bn2(z2)) ; out[i] = mean_{e -> i} m_e
-// which materialises eight [E, *] tensors.  Here one persistent CTA per SM (512 or 640 threads, ~220 KB
-// of shared memory) owns a contiguous range of target rows (CSR slots are sorted by target) and streams it in tiles
-// of 128 slots through mbarrier-connected warp roles -- no CTA-wide barrier inside the loop:
-//   gather      (16 warps; thread = 4 channels x 4 slots of every tile): P[dst] + Q[src] + W1c attr + b1 (Lin1
+// which materialises eight [E, *] tensors.  Here one persistent CTA per SM (640 threads, ~220 KB of shared memory) owns
+// a contiguous range of target rows (CSR slots are sorted by target) and streams it in tiles of 128 slots through
+// mbarrier-connected warp roles -- no CTA-wide barrier inside the loop:
+//   control     (one warp of a fourth warp group; setmaxnreg gives its registers to the gather warps):
+//        ring:  slot-ordered records (k_edge_records, once per layer call: P / Q byte offsets | attribute row, 16 B
+//               each) reach a 6-stage shared-memory ring as two TMA bulk copies per tile (cp.async.bulk + mbarrier
+//               complete_tx), five tiles ahead -- no thread touches an index on the way;
+//        MMA:   waits for the a1 stage of tile t and issues 24 tcgen05.mma.kind::tf32 (128 x 64 x 8; W2 hi/lo resident
+//               in shared memory, BN2 scale folded into its rows for F_AGG); z2 accumulates in TMEM (2 x 64 columns).
+//               The issue blocks for the ~1.3k cycles the tensor core needs (its operand reads are shared-memory
+//               bound), which is why no working warp does it (profiles/r1_t_edge_fused_agg_role_trace.txt);
+//   gather      (8 warps; thread = 4 channels x 8 slots of every tile): P[dst] + Q[src] + W1c attr + b1 (Lin1
 //               pre-reduced to node level: P = x (W1a-W1b)^T, Q = x W1b^T), BN1 + ReLU in packed fp32 pairs
 //               (FFMA2 / FADD2), truncating 3xTF32 hi/lo split written straight into the SWIZZLE_128B K-major a1
 //               stage of the tensor core (2 stages); the P / Q rows of tile t+1 are requested slot by slot while
-//               tile t is computed (4 slots x 2 rows per thread always in flight = 64 KB per SM); straight-line code
-//               with no polling inside, so the compiler interleaves the four slots; a1 never exists in HBM;
-//   ring        slot-ordered records (k_edge_records, once per layer call: P / Q byte offsets | attribute row, 16 B each)
-//               reach a 6-stage shared-memory ring as two TMA bulk copies per tile (cp.async.bulk + mbarrier
-//               complete_tx), issued by one elected lane five tiles ahead -- no thread touches an index on the way;
-//   epilogue    (4 or 8 warps, thread = one slot = one TMEM lane):
-//        MMA:   warp 0 waits for the a1 stage of tile t and issues 24 tcgen05.mma.kind::tf32 (128 x 64 x 8; W2 hi/lo
-//               resident in shared memory, BN2 scale folded into its rows for F_AGG) before it drains tile t-1, so
-//               the product of tile t overlaps the epilogue of t-1 and the gathers of t+1; z2 accumulates in TMEM
-//               (2 x 64 columns);
-//        drain: tcgen05.ld (32 lanes x 32 columns, twice) -> staging tile [slot][channel] in shared memory, then
+//               tile t is computed (8 slots x 2 rows per thread always in flight = 64 KB per SM) and prefetched into
+//               L2 three tiles ahead; straight-line code with no polling inside; a1 never exists in HBM;
+//   epilogue    (8 warps; thread = one slot = one TMEM lane, one column half):
+//        drain: tcgen05.ld (32 lanes x 32 columns) -> staging tile [slot][channel] in shared memory, then
 //        F_STATS: BatchNorm-2 batch statistics as column sums of the staging tile (training needs them before any
 //                 output exists),
-//        F_AGG:   BN2 + ReLU (+ edge weight) -> segmented mean per target row (4 threads x 16 channels per row, rows
+//        F_AGG:   BN2 + ReLU (+ edge weight) -> segmented mean per target row (8 threads x 8 channels per row, rows
 //                 finishing in the tile are written once as base + mean, the straddling row goes through a carry)
 //                 -- no atomics, fixed summation order, no read-modify-write of `out`,
 //        F_TAPE:  z1 / z2 for the backward pass (only when autograd needs them),
 //        F_Z1:    pass A -- only the gather half runs and accumulates the BatchNorm-1 statistics of z1.
 // Training forward = F_Z1 + F_STATS + F_AGG launches; nothing of size [E, C] touches HBM unless F_TAPE is set.
-// Measured bound (profiles/): issue slots of the gather warps and the SM <-> L1/L2 path of the row gathers; see
-// DESIGN.md section 3.
+// Other role splits (4 epilogue x 16 gather warps; MMAs issued by epilogue warp 0 or piece-wise by the gather warps)
+// are template parameters kept for experiments (YOLAT_EF_ROLES, YOLAT_EF_MG).  Measured bound: DESIGN.md section 3.1.
 #include <cstdlib>
 #include "common.cuh"
 #include "tc.cuh"
