@@ -183,3 +183,22 @@ def test_predict_slicing_matches_the_reference_loops():
             got = SparseCADGCN._build_data(data, sp, se, sb)
             for k in ('x', 'pos', 'bbox_idx', 'edge', 'e_attr', 'bbox', 'stat_feats'):
                 assert torch.equal(getattr(got, k), getattr(ref, k)), (seed, k)
+
+
+def test_fused_adam_has_no_cpu_path():
+    """optim.FusedAdam is CUDA-only like every other op: CPU parameters are rejected loudly, hyper-parameters are
+    validated like torch.optim.Adam's."""
+    import pytest
+    import torch
+    from yolat_vectorgraphicsrecognition_b200 import _lib
+    from yolat_vectorgraphicsrecognition_b200.optim import FusedAdam
+    p = torch.nn.Parameter(torch.randn(4, 4))
+    opt = FusedAdam([p], lr=1e-3, weight_decay=1e-4)
+    assert opt.param_groups[0]['lr'] == 1e-3 and opt.param_groups[0]['betas'] == (0.9, 0.999)
+    p.grad = torch.zeros_like(p)
+    with pytest.raises(_lib.YolatError):
+        opt.step()
+    with pytest.raises(ValueError):
+        FusedAdam([p], lr=-1.0)
+    with pytest.raises(ValueError):
+        FusedAdam([p], betas=(1.0, 0.999))
