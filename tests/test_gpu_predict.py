@@ -75,3 +75,24 @@ def test_predict_two_stage_equals_forward_on_oracle_slices():
     assert pred_cls.shape == ref.shape
     assert float((pred_cls - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
     assert slice_image_bbox[-1] == ref.shape[0]
+
+
+def test_predict_matches_the_unmodified_reference_golden():
+    """SparseCADGCN.predict on the device against the outputs of the UNMODIFIED reference's predict (fp64, CPU,
+    tests/golden/predict_forest.pt from oracle/make_golden_predict.py): the same proposals in the same order, logits
+    within the 1e-4 forward bar, boxes expanded by 5 % (:339-352), per-image slices identical."""
+    from types import SimpleNamespace
+    from util import load_golden, max_rel, FWD_TOL
+    from test_oracle import _forest_from_plain, _predict_case_state
+    for case in load_golden('predict_forest.pt'):
+        opt, model = _predict_case_state(case)
+        model = model.cuda().eval()
+        data = SimpleNamespace(**case['data'])
+        data.roots = _forest_from_plain(case['forest'])
+        with torch.no_grad():
+            pred_cls, pred_bbox, _, slice_bbox, slice_image_bbox, _ = model.predict(data, case['slices'])
+        assert tuple(pred_cls.shape) == tuple(case['pred_cls64'].shape)
+        assert max_rel(pred_cls, case['pred_cls64']) < FWD_TOL
+        assert max_rel(pred_bbox, case['pred_bbox64']) < 1e-6
+        assert [int(v) for v in torch.as_tensor(slice_bbox).reshape(-1)] == case['slice_bbox']
+        assert [int(v) for v in slice_image_bbox] == case['slice_image_bbox']

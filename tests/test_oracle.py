@@ -106,3 +106,72 @@ def test_reference_itself_when_present():
         assert max_rel(b, a) < 1e-5 and out[0].shape == (10, 17)
     finally:
         ref_loader.unload()
+
+
+def _forest_from_plain(plain):
+    from types import SimpleNamespace
+
+    def node(d):
+        v = {k: (tuple(x) if isinstance(x, list) else x) for k, x in d['value'].items()}
+        return SimpleNamespace(value=v, children=[node(c) for c in d['children']])
+    return [node(r) for r in plain]
+
+
+def _predict_case_state(case):
+    """The case's weights: same seed + same construction order as the reference => bit-identical init (checked)."""
+    import torch
+    from yolat_vectorgraphicsrecognition_b200 import synth
+    from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
+    opt = synth.make_opt(n_classes=case['n_classes'])
+    torch.manual_seed(case['seed'])
+    model = arch.SparseCADGCN(opt)
+    sd = model.state_dict()
+    for k, v in case['state_checksum'].items():
+        assert abs(float(sd[k].double().sum()) - v) <= 1e-6 * max(1.0, abs(v)), k
+    return opt, model
+
+
+def test_predict_restatement_matches_reference_golden():
+    """oracle/predict_slicing.py + oracle/restatement.py against the UNMODIFIED reference's SparseCADGCN.predict
+    (tests/golden/predict_forest.pt, generated by oracle/make_golden_predict.py): same proposals classified, in the
+    same order, with the same logits -- this pins the slicing restatement the GPU tests are checked against."""
+    import torch
+    from types import SimpleNamespace
+    from oracle import predict_slicing as P, restatement as R
+    for case in load_golden('predict_forest.pt'):
+        opt, model = _predict_case_state(case)
+        state = R.clone_state(model.state_dict(), torch.float64, requires_grad=False)
+        data = SimpleNamespace(**{k: (v.double() if v.is_floating_point() else v) for k, v in case['data'].items()})
+        data.roots = _forest_from_plain(case['forest'])
+        slices = case['slices']
+        n_img = len(slices['roots']) - 1
+        root_nodes = [(r, i) for i in range(n_img) for r in data.roots[slices['roots'][i]:slices['roots'][i + 1]]]
+        sp, se, sb = P.ranges(root_nodes, slices)
+        nd = P.build_data(data, sp, se, sb)
+        with torch.no_grad():
+            root_cls = R.cadgcn_forward(state, opt, nd.x, nd.edge, nd.e_attr, nd.bbox_idx, training=False)
+        has_object = root_cls.max(1)[1] == opt.n_classes - 1
+        child_nodes, per_image, count = [], [], 0
+        for i in range(n_img):
+            n_root = n_child = 0
+            for root in data.roots[slices['roots'][i]:slices['roots'][i + 1]]:
+                if has_object[count]:
+                    child_nodes += [(c, i) for c in root.children]
+                    n_child += len(root.children)
+                count += 1
+                n_root += 1
+            per_image.append((n_root, n_child))
+        assert child_nodes, 'fixture should exercise the second stage'
+        sp2, se2, sb2 = P.ranges(child_nodes, slices)
+        nd2 = P.build_data(data, sp2, se2, sb2)
+        with torch.no_grad():
+            child_cls = R.cadgcn_forward(state, opt, nd2.x, nd2.edge, nd2.e_attr, nd2.bbox_idx, training=False)
+        rows, boxes, r0, c0 = [], [], 0, 0
+        for n_root, n_child in per_image:
+            rows += [root_cls[r0:r0 + n_root], child_cls[c0:c0 + n_child]]
+            boxes += sb[r0:r0 + n_root] + sb2[c0:c0 + n_child]
+            r0 += n_root; c0 += n_child
+        got = torch.cat(rows, 0)
+        assert got.shape == case['pred_cls64'].shape
+        assert float((got - case['pred_cls64']).abs().max()) < 1e-9
+        assert boxes == case['slice_bbox']
