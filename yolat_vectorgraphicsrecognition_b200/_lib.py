@@ -139,18 +139,29 @@ def f32c(t):
 
 
 class _Workspace(object):
-    """One grow-only fp32 scratch buffer per device, shared by all calls on the same stream order."""
+    """One grow-only fp32 scratch buffer per device, shared by all calls on the same stream order.
+
+    A CUDA graph captured by `GraphedStep` bakes the buffer's device address into its kernel nodes, so a buffer that
+    has been handed out is NEVER released: when a larger request arrives the old block is retired (kept referenced for
+    the life of the process) and a bigger one becomes current.  Graphs captured earlier keep replaying into their own,
+    still-owned block; nothing else can be allocated on top of it."""
 
     def __init__(self):
         self.buf = {}
+        self.retired = {}
 
     def get(self, n_floats, device):
         n_floats = max(int(n_floats), 64)
         b = self.buf.get(device)
         if b is None or b.numel() < n_floats:
+            if b is not None:
+                self.retired.setdefault(device, []).append(b)
             b = torch.empty(int(n_floats * 1.25), dtype=torch.float32, device=device)
             self.buf[device] = b
         return b
+
+    def retired_bytes(self, device):
+        return sum(t.numel() * 4 for t in self.retired.get(device, []))
 
 
 workspace = _Workspace()
