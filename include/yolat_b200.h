@@ -217,6 +217,10 @@ int yolat_softmax_xent_bwd(const float* prob, int64_t B, int ncls, const int64_t
 int yolat_adam_chunk(void);
 int yolat_adam_step(const uint64_t* table, const int32_t* count, int64_t n_chunks, double* state, double lr, double beta1,
                     double beta2, double eps, double weight_decay, double grad_scale, void* stream);
+/* Same update with the hyper-parameters on the device: state is 9 doubles, [3..8] = lr, beta1, beta2, eps,
+ * weight_decay, grad_scale, read by the kernels at execution time -- a captured step follows torch's StepLR
+ * (train.py:214) and restored checkpoints without re-capture; the host rewrites state[3..8] when they change. */
+int yolat_adam_step_dev(const uint64_t* table, const int32_t* count, int64_t n_chunks, double* state, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Proposal slicing of SparseCADGCN.predict on the device (architecture3cc_rpn_gp_iter2.py:153-234: python range

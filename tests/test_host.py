@@ -161,11 +161,11 @@ def _proposal_forest(seed, n_images=2):
 
 
 def test_predict_slicing_matches_the_reference_loops():
-    """The vectorised `_ranges` / `_build_data` of the host mirror against the plain-Python restatement of the
+    """The vectorised host mirror (oracle/host_slicing.py) against the plain-Python restatement of the
     reference's loops (oracle/predict_slicing.py; architecture3cc_rpn_gp_iter2.py:153-234), on roots and on children."""
     import torch
     from oracle import predict_slicing as P
-    from yolat_vectorgraphicsrecognition_b200.architecture3cc_rpn_gp_iter2 import SparseCADGCN
+    from oracle import host_slicing as HS
     for seed in (0, 1, 2):
         data, slices = _proposal_forest(seed)
         root_nodes, child_nodes = [], []
@@ -178,9 +178,9 @@ def test_predict_slicing_matches_the_reference_loops():
                 continue
             sp_ref, se_ref, sb_ref = P.ranges(nodes, slices)
             ref = P.build_data(data, sp_ref, se_ref, sb_ref)
-            sp, se, sb = SparseCADGCN._ranges(nodes, slices, None)
+            sp, se, sb = HS.ranges(nodes, slices, None)
             assert list(sp) == sp_ref and list(se) == se_ref and list(sb) == sb_ref
-            got = SparseCADGCN._build_data(data, sp, se, sb)
+            got = HS.build_data(data, sp, se, sb)
             for k in ('x', 'pos', 'bbox_idx', 'edge', 'e_attr', 'bbox', 'stat_feats'):
                 assert torch.equal(getattr(got, k), getattr(ref, k)), (seed, k)
 

@@ -79,6 +79,7 @@ _SIGS = {
     'yolat_adam_chunk': (C.c_int, []),
     'yolat_adam_step': (C.c_int, [vp, vp, i64, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_double, vp]),
+    'yolat_adam_step_dev': (C.c_int, [vp, vp, i64, vp, vp]),
 }
 
 _lib = None

@@ -30,8 +30,16 @@ class GraphedStep(object):
 
     def __init__(self, model, criterion, warmup=3, extra=None):
         """`extra(loss)` (optional) is called inside the captured region after backward -- e.g. a fused
-        optimizer step or the data-parallel gradient all-reduce -- and must be capture-safe."""
+        optimizer step or the data-parallel gradient all-reduce -- and must be capture-safe.  It is NOT run during the
+        eager warm-up steps of a capture (they would be hidden optimizer updates / extra collectives); if its owner
+        (`extra.__self__`) has `prepare()` it is called once here (allocations that are illegal under capture), and
+        `sync_hyperparams()` before every capture and replay (device-resident learning rate of optim.FusedAdam).
+        With a collective inside `extra`, every rank must meet a new batch shape at the same step: capture is a
+        collective event."""
         self.model, self.criterion, self.warmup, self.extra = model, criterion, int(warmup), extra
+        self._extra_owner = getattr(extra, '__self__', None)
+        if hasattr(self._extra_owner, 'prepare'):
+            self._extra_owner.prepare()
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.device = next(model.parameters()).device
         if self.device.type != 'cuda':
@@ -47,11 +55,15 @@ class GraphedStep(object):
             return batch.signature()
         return tuple((f, tuple(getattr(batch, f).shape), getattr(batch, f).dtype) for f in _FIELDS)
 
-    def _eager(self, static):
+    def _sync_extra(self):
+        if hasattr(self._extra_owner, 'sync_hyperparams'):
+            self._extra_owner.sync_hyperparams()
+
+    def _eager(self, static, run_extra=True):
         out = self.model(static, None)
         loss = self.criterion(out, static)['loss']
         loss.backward()
-        if self.extra is not None:
+        if run_extra and self.extra is not None:
             self.extra(loss)
         return loss, out[0]
 
@@ -81,10 +93,12 @@ class GraphedStep(object):
             for _ in range(self.warmup):
                 for p in self.params:
                     p.grad = None
-                self._eager(static)
+                self._eager(static, run_extra=False)
         torch.cuda.current_stream(self.device).wait_stream(side)
-        # NOTE: the warm-up steps are real training-mode forwards: they update the BN running buffers the same
-        # way `warmup` extra iterations on this batch would.  Restore them so capture has no side effect.
+        self._sync_extra()
+        # NOTE: the warm-up steps are real training-mode forwards + backwards (without `extra`): they update the BN
+        # running buffers the same way `warmup` extra iterations on this batch would; _entry() restores them, so a
+        # capture leaves parameters, optimizer state and buffers untouched.
         graph = torch.cuda.CUDAGraph()
         for p in self.params:
             p.grad = None
@@ -148,6 +162,7 @@ class GraphedStep(object):
                 self._stage(entry, batch)
         for p, g in zip(self.params, entry.grads):
             p.grad = g
+        self._sync_extra()
         entry.graph.replay()
         entry.done.record(cur)
         self.last_logits = entry.logits

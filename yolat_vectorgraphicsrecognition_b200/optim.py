@@ -6,7 +6,8 @@ the gradient, bias-corrected moments, eps added after the square root), same `pa
 `torch.optim.lr_scheduler.StepLR` (train.py:214) and the same `state_dict()` layout (`state[i] = {step, exp_avg,
 exp_avg_sq}`), so `load_pretrained_optimizer` (utils/ckpt_util.py) keeps working.  The update itself is two kernel
 launches over a chunk table (csrc/adam.cu) instead of ~100, reads its step counter from the device and is therefore
-capturable: pass `FusedAdam.step` as `GraphedStep(extra=...)` to make it part of the replayed step.
+capturable: pass `FusedAdam.step` as `GraphedStep(extra=...)` to make it part of the replayed step.  Learning rate,
+betas, eps and weight decay live in device memory (`sync_hyperparams`), so a captured step follows a scheduler.
 
 No CPU path: parameters must live on a CUDA device.
 """
@@ -42,7 +43,7 @@ class FusedAdam(torch.optim.Optimizer):
             n = sum(p.numel() for p in ps)
             m = torch.zeros(n, dtype=torch.float32, device=dev)
             v = torch.zeros(n, dtype=torch.float32, device=dev)
-            state = torch.zeros(3, dtype=torch.float64, device=dev)
+            state = torch.zeros(9, dtype=torch.float64, device=dev)   # step | derived | hyper-parameters
             off, views = 0, []
             for p in ps:
                 views.append((m[off:off + p.numel()].view_as(p), v[off:off + p.numel()].view_as(p)))
@@ -62,11 +63,37 @@ class FusedAdam(torch.optim.Optimizer):
                     base.append((i, c, off + c))
                 off += p.numel()
             count = torch.tensor(counts, dtype=torch.int32).to(dev)
-            pool = [(torch.empty(len(counts), 4, dtype=torch.int64).pin_memory(),
-                     torch.empty(len(counts), 4, dtype=torch.int64, device=dev)) for _ in range(self.MAX_GRAD_SETS)]
-            self._groups.append(dict(params=ps, m=m, v=v, state=state, count=count, base=base, pool=pool, tables={}))
+            # Chunk tables: one (pinned, device) pair per set of gradient addresses.  A pair consumed under CUDA-graph
+            # capture is PERMANENT (the graph re-executes its pinned -> device copy on every replay, so neither buffer
+            # may ever be rewritten); eager steps cycle through a small ring whose pinned side is only rewritten after
+            # the event recorded behind its previous copy has completed.
+            def pair():
+                return (torch.empty(len(counts), 4, dtype=torch.int64).pin_memory(),
+                        torch.empty(len(counts), 4, dtype=torch.int64, device=dev))
+            captured = [pair() for _ in range(self.MAX_CAPTURED_SETS)]
+            eager = [pair() + (torch.cuda.Event(),) for _ in range(self.EAGER_RING)]
+            hyper_host = torch.zeros(6, dtype=torch.float64).pin_memory()
+            self._groups.append(dict(params=ps, m=m, v=v, state=state, count=count, base=base, captured=captured,
+                                     n_captured=0, eager=eager, eager_keys=[None] * self.EAGER_RING, eager_next=0,
+                                     tables={}, hyper_host=hyper_host, hyper_event=None, hyper_last=None))
 
-    MAX_GRAD_SETS = 4
+    MAX_CAPTURED_SETS = 32     # gradient-address sets that CUDA graphs may hold (2 input slots x 16 batch shapes)
+    EAGER_RING = 2
+
+    def prepare(self):
+        """Allocate the flat moment buffers, the device state and the (pinned) table pool now -- call before capturing
+        `step` in a CUDA graph (GraphedStep does): page-locked allocations are not legal while a stream captures."""
+        if self._groups is None:
+            self._prepare()
+
+    def _rows(self, g):
+        for p in g['params']:
+            if p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
+                raise _lib.YolatError('FusedAdam: gradients must be contiguous fp32 tensors')
+        ps = g['params']
+        mp, vp = g['m'].data_ptr(), g['v'].data_ptr()
+        rows = [(ps[i].data_ptr() + 4 * c, ps[i].grad.data_ptr() + 4 * c, mp + 4 * o, vp + 4 * o) for i, c, o in g['base']]
+        return torch.tensor(rows, dtype=torch.int64)       # (addresses are below 2^63: bit-exact in int64)
 
     def _table(self, g):
         """Device chunk table for the current gradient tensors, cached per set of gradient addresses."""
@@ -74,19 +101,52 @@ class FusedAdam(torch.optim.Optimizer):
         hit = g['tables'].get(key)
         if hit is not None:
             return hit
-        if len(g['tables']) >= len(g['pool']):
-            g['tables'].clear()                       # gradient tensors were re-allocated (eager training): start over
-        pinned, dev = g['pool'][len(g['tables'])]
-        for p in g['params']:
-            if p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
-                raise _lib.YolatError('FusedAdam: gradients must be contiguous fp32 tensors')
-        ps = g['params']
-        mp, vp = g['m'].data_ptr(), g['v'].data_ptr()
-        rows = [(ps[i].data_ptr() + 4 * c, ps[i].grad.data_ptr() + 4 * c, mp + 4 * o, vp + 4 * o) for i, c, o in g['base']]
-        pinned.copy_(torch.tensor(rows, dtype=torch.int64))       # (addresses are below 2^63: bit-exact in int64)
-        dev.copy_(pinned, non_blocking=True)
-        g['tables'][key] = dev
-        return dev
+        dev = g['state'].device
+        if torch.cuda.is_current_stream_capturing():
+            if g['n_captured'] >= len(g['captured']):
+                raise _lib.YolatError('FusedAdam: more than %d gradient sets captured in CUDA graphs' % len(g['captured']))
+            pinned, table = g['captured'][g['n_captured']]
+            g['n_captured'] += 1
+            pinned.copy_(self._rows(g))
+            table.copy_(pinned, non_blocking=True)        # a memcpy node: re-executed (same bytes) on every replay
+            g['tables'][key] = table                      # never evicted
+            return table
+        i = g['eager_next']
+        g['eager_next'] = (i + 1) % len(g['eager'])
+        pinned, table, ev = g['eager'][i]
+        if g['eager_keys'][i] is not None:
+            g['tables'].pop(g['eager_keys'][i], None)
+            ev.synchronize()                              # the previous copy out of this pinned buffer has executed
+        pinned.copy_(self._rows(g))
+        table.copy_(pinned, non_blocking=True)
+        ev.record(torch.cuda.current_stream(dev))
+        g['eager_keys'][i] = key
+        g['tables'][key] = table
+        return table
+
+    def sync_hyperparams(self, grad_scale=1.0):
+        """Write lr / betas / eps / weight_decay / grad_scale of every param group into its device state (one 48-byte
+        asynchronous copy, only when a value changed).  `step()` calls it when it runs eagerly; a step captured in a
+        CUDA graph reads the device values at replay time, so call this (GraphedStep does) before each replay."""
+        if self._groups is None:
+            self._prepare()
+        for group, g in zip(self.param_groups, self._groups):
+            if g is None:
+                continue
+            b1, b2 = group['betas']
+            vals = (float(group['lr']), float(b1), float(b2), float(group['eps']), float(group['weight_decay']),
+                    float(grad_scale))
+            if vals == g['hyper_last']:
+                continue
+            dev = g['state'].device
+            if g['hyper_event'] is not None:
+                g['hyper_event'].synchronize()            # the previous copy has read the pinned buffer
+            g['hyper_host'].copy_(torch.tensor(vals, dtype=torch.float64))
+            g['state'][3:9].copy_(g['hyper_host'], non_blocking=True)
+            if g['hyper_event'] is None:
+                g['hyper_event'] = torch.cuda.Event()
+            g['hyper_event'].record(torch.cuda.current_stream(dev))
+            g['hyper_last'] = vals
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale=1.0):
@@ -97,16 +157,19 @@ class FusedAdam(torch.optim.Optimizer):
         if self._groups is None:
             self._prepare()
         lib = _lib.lib()
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_hyperparams(grad_scale)
+        elif any(g is not None and g['hyper_last'] is None for g in self._groups):
+            raise _lib.YolatError('FusedAdam.step captured before sync_hyperparams(): call prepare() + sync_hyperparams() '
+                                  'first (GraphedStep does)')
         for group, g in zip(self.param_groups, self._groups):
             if g is None:
                 continue
             if any(p.grad is None for p in g['params']):
                 raise _lib.YolatError('FusedAdam.step: every parameter of the group needs a gradient')
             table, count, n = self._table(g), g['count'], len(g['base'])
-            b1, b2 = group['betas']
-            _lib.check(lib.yolat_adam_step(table.data_ptr(), count.data_ptr(), n, g['state'].data_ptr(), float(group['lr']),
-                                       float(b1), float(b2), float(group['eps']), float(group['weight_decay']),
-                                       float(grad_scale), torch.cuda.current_stream(g['state'].device).cuda_stream), 'yolat_adam_step')
+            _lib.check(lib.yolat_adam_step_dev(table.data_ptr(), count.data_ptr(), n, g['state'].data_ptr(),
+                                               torch.cuda.current_stream(g['state'].device).cuda_stream), 'yolat_adam_step_dev')
         return loss
 
     def load_state_dict(self, state_dict):
