@@ -46,6 +46,9 @@ int64_t yolat_launch_count(void);
 #define YOLAT_PROF_EDGE_FUSED_STATS 1  /* ef::k_edge_fused<F_STATS>  (K-EDGE pass B)            */
 #define YOLAT_PROF_EDGE_FUSED_AGG 2    /* ef::k_edge_fused<F_AGG>    (K-EDGE pass C, the scatter) */
 #define YOLAT_PROF_GEMM 3              /* tc::k_tc_gemm (any mode)                              */
+#define YOLAT_PROF_EDGE_BWD_D1 4       /* eb::k_edge_bwd<D1>   (K-EDGE backward: BN2 statistics)  */
+#define YOLAT_PROF_EDGE_BWD_D2T 5      /* eb::k_edge_bwd<D2T>  (dW2, BN1 statistics, sums by target) */
+#define YOLAT_PROF_EDGE_BWD_D2S 6      /* eb::k_edge_bwd<D2S>  (sums by source)                    */
 int yolat_prof_enable(int on);
 int yolat_prof_read(int id, int64_t* launches, double* total_ms);
 
@@ -104,6 +107,11 @@ typedef struct {         /* gradient outputs, same shapes as the parameters; any
 } yolat_gp2_grads;
 
 int64_t yolat_gp2_tape_floats(int64_t N, int64_t E, int Cin, int Cn, int C);
+/* Tape size for a given `training` mode word of yolat_gp2_fwd / _bwd.  Training-mode calls at C = 64 run tape-free:
+ * the tape holds node-level tensors only (node-branch pre-activation, BN statistic blocks, P | Q) and the backward
+ * recomputes every per-edge quantity on chip (csrc/edge_bwd.cu); other calls keep z1 / z2 [E, C] for the backward.
+ * yolat_gp2_tape_floats(...) == yolat_gp2_tape_floats_mode(..., 0) is an upper bound valid for every mode. */
+int64_t yolat_gp2_tape_floats_mode(int64_t N, int64_t E, int Cin, int Cn, int C, int mode);
 int64_t yolat_gp2_fwd_ws_floats(int64_t N, int64_t E, int Cin, int Cn, int C);
 int64_t yolat_gp2_bwd_ws_floats(int64_t N, int64_t E, int Cin, int Cn, int C);
 

@@ -48,6 +48,7 @@ _SIGS = {
     'yolat_segments_ints': (i64, [i64, i64]),
     'yolat_segments_build': (C.c_int, [vp, i64, i64, vp, vp]),
     'yolat_gp2_tape_floats': (i64, [i64, i64, i32, i32, i32]),
+    'yolat_gp2_tape_floats_mode': (i64, [i64, i64, i32, i32, i32, i32]),
     'yolat_gp2_fwd_ws_floats': (i64, [i64, i64, i32, i32, i32]),
     'yolat_gp2_bwd_ws_floats': (i64, [i64, i64, i32, i32, i32]),
     'yolat_gp2_fwd': (C.c_int, [C.POINTER(Gp2Params), i32, i32, i32, vp, i64, vp, i64, vp, vp, vp, i64, i64, i32,

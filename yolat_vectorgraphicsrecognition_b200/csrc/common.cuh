@@ -248,6 +248,19 @@ int edge_fused(const GraphView& g, int64_t N, int64_t E, int flags, const float*
                const float* stat2, const float* ew, float* z1, float* z2, float* part, const float* base, int64_t ldb,
                float* out, int64_t ldo, cudaStream_t st);
 
+// edge_bwd.cu: the tape-free backward of the fused edge path (training mode, C == 64): recompute passes D1 / D2T / D2S
+struct EdgeBwdWs {
+  int grid;
+  float *rec_t, *rec_s, *Ut, *Xt, *Us, *Xs, *part1, *part_tx, *part2, *part_T, *part_w2, *bstat2, *bstat1;
+};
+int edge_bwd_grid(int64_t E);
+void edge_bwd_layout(Arena& ws, int64_t N, int64_t E, EdgeBwdWs* o);
+int edge_bwd_fused(const GraphView& g, int64_t N, int64_t E, const float* pq, int64_t ldpq, const float* attr,
+                   const float* w1, int Cin, const float* b1, const float* stat1, const float* gamma1, const float* w2,
+                   const float* b2, const float* stat2, const float* gamma2, const float* ew, const float* g_out,
+                   int64_t ldgo, const EdgeBwdWs& w, float* dpq, float* dw1c, float* dw2, float* db1, float* dg1,
+                   float* dbe1, float* db2, float* dg2, float* dbe2, cudaStream_t st);
+
 int colsum(const float* a, int64_t lda, int64_t M, int C, float* out, Arena& ws, cudaStream_t st);
 int fill_zero(float* p, int64_t n, cudaStream_t st);
 

@@ -18,16 +18,19 @@
 namespace yolat {
 
 struct Gp2Tape {
-  float* z1; float* z2; float* zn; float* stat1; float* stat2; float* statn;
+  float* z1; float* z2; float* zn; float* stat1; float* stat2; float* statn; float* pq;
 };
 
-static void gp2_tape_layout(Arena& t, int64_t N, int64_t E, int C, Gp2Tape* o) {
-  o->z1 = t.take(E * C);
-  o->z2 = t.take(E * C);
+// `lite`: the tape of the recompute backward (edge_bwd.cu) -- no per-edge activation, only node-level tensors:
+// the node branch's pre-activation, the three BN statistic blocks and P | Q.
+static void gp2_tape_layout(Arena& t, int64_t N, int64_t E, int C, bool lite, Gp2Tape* o) {
+  o->z1 = lite ? nullptr : t.take(E * C);
+  o->z2 = lite ? nullptr : t.take(E * C);
   o->zn = t.take(N * C);
   o->stat1 = t.take(4 * C);
   o->stat2 = t.take(4 * C);
   o->statn = t.take(4 * C);
+  o->pq = lite ? t.take(N * 2 * C) : nullptr;
 }
 
 // YOLAT_EDGE=unfused selects the three-kernel edge path (z1 -> GEMM -> aggregate) instead of edge_fused.cu
@@ -84,6 +87,22 @@ static void join_branch(Branches* b, int i, cudaStream_t st) {
   cudaStreamWaitEvent(st, b->join[i], 0);
 }
 
+// Training-mode calls with the fused K-EDGE kernels available run tape-free in both directions: the forward keeps
+// only statistics + P | Q, the backward recomputes (edge_bwd.cu).  YOLAT_EDGE_BWD=tape selects the round-1 schedule
+// (z1 / z2 tape + multi-kernel backward) for A/B comparisons; eval-mode backward and C != 64 always use it.
+static bool edge_bwd_recompute_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YOLAT_EDGE_BWD");
+    v = (e && e[0] == 't') ? 0 : 1;
+  }
+  return v == 1;
+}
+static bool gp2_lite(int64_t N, int64_t E, int C, int training) {
+  return training && E > 0 && edge_fused_supported(C) && edge_fused_fits(N, 3 * C) && gemm_fused_enabled() &&
+         edge_bwd_recompute_enabled();
+}
+
 static bool gp2_channels_ok(int Cin, int Cn, int C) {
   return (C == 32 || C == 64 || C == 128) && Cin >= 1 && Cn >= 1;
 }
@@ -94,9 +113,10 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
                         float* xnode_out, int64_t ldxo, Arena& tape, Arena& ws, cudaStream_t st) {
   const bool dry = ws.dry();
   const int training = (mode & YOLAT_GP2_TRAINING) ? 1 : 0;
-  const bool no_tape = (mode & YOLAT_GP2_NO_TAPE) != 0;   // forward only: z1 / z2 are never written
+  const bool lite = gp2_lite(N, E, C, training);
+  const bool no_tape = lite || (mode & YOLAT_GP2_NO_TAPE) != 0;   // z1 / z2 are never written
   Gp2Tape t;
-  gp2_tape_layout(tape, N, E, C, &t);
+  gp2_tape_layout(tape, N, E, C, lite, &t);
   // Fused path: one GEMM x [Wp; Wq; Wr]^T -> P | Q | lin_r(x) (row stride 3C); the aggregation adds the lin_r column
   // block while writing `out`.  Unfused path (C = 32 / 128): lin_r goes straight to `out`, P | Q has row stride 2C.
   // (Folding lin_r into the P | Q GEMM -- kFusePqr -- was measured slower at the > L2 scale: the third 64-column block
@@ -107,7 +127,7 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
   const int ldpq = pqr ? 3 * C : 2 * C;
   float* wpq = ws.take((int64_t)3 * C * Cin);
   float* bias3 = ws.take(3 * C);
-  float* pq = ws.take(N * ldpq);
+  float* pq = lite ? t.pq : ws.take(N * ldpq);
   const int nparts = edge_z1_nparts(N);
   float* part1 = ws.take((int64_t)nparts * 2 * C);
   if (!dry && (ws.overflow || tape.overflow)) return YOLAT_ERR_WORKSPACE;
@@ -207,8 +227,9 @@ static int gp2_bwd_impl(const yolat_gp2_params* p, const yolat_gp2_grads* gr, in
                         const float* g_xnode, int64_t ldgx, float* dx, int64_t lddx, float* dx_node, int64_t lddxn,
                         int accumulate_dx, Arena& tape, Arena& ws, cudaStream_t st) {
   const bool dry = ws.dry();
+  const bool lite = gp2_lite(N, E, C, training);
   Gp2Tape t;
-  gp2_tape_layout(tape, N, E, C, &t);
+  gp2_tape_layout(tape, N, E, C, lite, &t);
   const int ld1 = 2 * Cin + 4;
   yolat_gp2_grads G{};
   if (!dry) G = *gr;
@@ -257,7 +278,35 @@ static int gp2_bwd_impl(const yolat_gp2_params* p, const yolat_gp2_grads* gr, in
   }
 
   // ---- edge path ------------------------------------------------------------------------------------
-  if (E > 0) {
+  if (lite) {
+    // Recompute backward (edge_bwd.cu): three fused passes over the slots, nothing of size [E, C] in HBM.
+    EdgeBwdWs bw;
+    edge_bwd_layout(ws, N, E, &bw);
+    float* dpq = ws.take(N * 2 * C);
+    float* wpq = ws.take((int64_t)2 * C * Cin);
+    float* dwpq = ws.take((int64_t)2 * C * Cin);
+    float* dw1c = ws.take((int64_t)C * 4);
+    if (!dry) {
+      if (ws.overflow) return YOLAT_ERR_WORKSPACE;
+      YOLAT_TRY(edge_bwd_fused(g, N, E, t.pq, 2 * C, attr, p->w1, Cin, p->b1, t.stat1, p->bn1.w, p->w2, p->b2, t.stat2,
+                               p->bn2.w, ew, g_out, ldgo, bw, dpq, dw1c, G.w2, G.b1, G.bn1_w, G.bn1_b, G.b2, G.bn2_w,
+                               G.bn2_b, st));
+    }
+    if (G.w1 || dry) {   // dWpq = dPQ^T x ; dW1 = [dWp | dWq - dWp | dW1c]
+      GemmArgs a{};
+      a.A = dpq; a.lda = 2 * C; a.B = x; a.ldb = ldx; a.C = dwpq; a.ldc = Cin; a.M = 2 * C; a.N = Cin; a.K = N;
+      YOLAT_TRY(gemm(a, GEMM_TN, ws, st));
+      if (!dry && G.w1) YOLAT_TRY(edge_assemble_dw1(dwpq, dw1c, Cin, C, G.w1, st));
+    }
+    if (dx || dry) {     // dx += dPQ Wpq  (after lin_r's own contribution to dx)
+      if (br) join_branch(br, 1, st);
+      if (!dry) YOLAT_TRY(edge_prep_wpq(p->w1, Cin, C, wpq, nullptr, nullptr, nullptr, st));
+      GemmArgs a{};
+      a.A = dpq; a.lda = 2 * C; a.B = wpq; a.ldb = Cin; a.C = dx; a.ldc = lddx;
+      a.M = (int)N; a.N = Cin; a.K = 2 * C; a.accumulate = acc_dx;
+      YOLAT_TRY(gemm(a, GEMM_NN, ws, st));
+    }
+  } else if (E > 0) {
     float* dz2 = ws.take(E * C);
     float* dz1 = ws.take(E * C);
     float* dpq = ws.take(N * 2 * C);
@@ -332,27 +381,39 @@ using namespace yolat;
 extern "C" {
 
 int64_t yolat_gp2_tape_floats(int64_t N, int64_t E, int Cin, int Cn, int C) {
+  return yolat_gp2_tape_floats_mode(N, E, Cin, Cn, C, 0);
+}
+
+int64_t yolat_gp2_tape_floats_mode(int64_t N, int64_t E, int Cin, int Cn, int C, int mode) {
   (void)Cin; (void)Cn;
   Arena t(nullptr, 0);
   Gp2Tape o;
-  gp2_tape_layout(t, N, E, C, &o);
+  gp2_tape_layout(t, N, E, C, gp2_lite(N, E, C, mode & YOLAT_GP2_TRAINING), &o);
   return t.off;
 }
 
 int64_t yolat_gp2_fwd_ws_floats(int64_t N, int64_t E, int Cin, int Cn, int C) {
   if (!gp2_channels_ok(Cin, Cn, C)) return -1;
-  Arena tape(nullptr, 0), ws(nullptr, 0);
-  gp2_fwd_impl(nullptr, Cin, Cn, C, nullptr, Cin, nullptr, Cn, nullptr, nullptr, nullptr, N, E, 1, nullptr, C, nullptr, C,
-               tape, ws, nullptr);
-  return ws.off;
+  int64_t need = 0;
+  for (int mode = 0; mode < 2; ++mode) {     // the larger of the eval- and the training-mode plan
+    Arena tape(nullptr, 0), ws(nullptr, 0);
+    gp2_fwd_impl(nullptr, Cin, Cn, C, nullptr, Cin, nullptr, Cn, nullptr, nullptr, nullptr, N, E, mode, nullptr, C, nullptr,
+                 C, tape, ws, nullptr);
+    need = ws.off > need ? ws.off : need;
+  }
+  return need;
 }
 
 int64_t yolat_gp2_bwd_ws_floats(int64_t N, int64_t E, int Cin, int Cn, int C) {
   if (!gp2_channels_ok(Cin, Cn, C)) return -1;
-  Arena tape(nullptr, 0), ws(nullptr, 0);
-  gp2_bwd_impl(nullptr, nullptr, Cin, Cn, C, nullptr, Cin, nullptr, Cn, nullptr, nullptr, nullptr, N, E, 1, nullptr, C,
-               nullptr, C, nullptr, Cin, nullptr, Cn, 0, tape, ws, nullptr);
-  return ws.off;
+  int64_t need = 0;
+  for (int training = 0; training < 2; ++training) {
+    Arena tape(nullptr, 0), ws(nullptr, 0);
+    gp2_bwd_impl(nullptr, nullptr, Cin, Cn, C, nullptr, Cin, nullptr, Cn, nullptr, nullptr, nullptr, N, E, training, nullptr,
+                 C, nullptr, C, nullptr, Cin, nullptr, Cn, 0, tape, ws, nullptr);
+    need = ws.off > need ? ws.off : need;
+  }
+  return need;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -364,7 +425,7 @@ int yolat_gp2_fwd(const yolat_gp2_params* p, int Cin, int Cn, int C, const float
   if (!p || !x || !x_node || !graph || !out || !xnode_out || !tape || !ws || N <= 0 || E < 0) return YOLAT_ERR_INVALID;
   if (E > 0 && (!attr || !aligned16(attr))) return YOLAT_ERR_INVALID;
   if (!gp2_channels_ok(Cin, Cn, C)) return YOLAT_ERR_UNSUPPORTED;
-  if (tape_floats < yolat_gp2_tape_floats(N, E, Cin, Cn, C)) return YOLAT_ERR_WORKSPACE;
+  if (tape_floats < yolat_gp2_tape_floats_mode(N, E, Cin, Cn, C, training)) return YOLAT_ERR_WORKSPACE;
   Arena t(tape, tape_floats), w(ws, ws_floats);
   return gp2_fwd_impl(p, Cin, Cn, C, x, ldx, x_node, ldxn, attr, edge_weight, graph, N, E, training, out, ldo, xnode_out,
                       ldxo, t, w, (cudaStream_t)stream);
@@ -378,7 +439,7 @@ int yolat_gp2_bwd(const yolat_gp2_params* p, const yolat_gp2_grads* g, int Cin, 
   if (!p || !g || !x || !x_node || !graph || !tape || !ws || !g_out || !g_xnode || N <= 0 || E < 0) return YOLAT_ERR_INVALID;
   if (E > 0 && (!attr || !aligned16(attr))) return YOLAT_ERR_INVALID;
   if (!gp2_channels_ok(Cin, Cn, C)) return YOLAT_ERR_UNSUPPORTED;
-  Arena t(const_cast<float*>(tape), yolat_gp2_tape_floats(N, E, Cin, Cn, C)), w(ws, ws_floats);
+  Arena t(const_cast<float*>(tape), yolat_gp2_tape_floats_mode(N, E, Cin, Cn, C, training)), w(ws, ws_floats);
   return gp2_bwd_impl(p, g, Cin, Cn, C, x, ldx, x_node, ldxn, attr, edge_weight, graph, N, E, training, g_out, ldgo,
                       g_xnode, ldgx, dx, lddx, dx_node, lddxn, accumulate_dx, t, w, (cudaStream_t)stream);
 }

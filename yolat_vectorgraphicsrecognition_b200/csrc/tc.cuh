@@ -68,6 +68,14 @@ __device__ __forceinline__ void mbar_wait_park(uint32_t addr, uint32_t parity) {
     if (spins > 200000000) asm volatile("trap;");
   }
 }
+// Same parking wait with a wall-clock bound (~2 s of SM cycles): a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t addr, uint32_t parity) {
+  if (mbar_try_wait(addr, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(addr, parity, 20000u)) {
+    if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
+  }
+}
 // ---- TMA bulk copy (cp.async.bulk, 1-D): global -> shared, completion counted in bytes on an mbarrier -------------
 __device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
@@ -126,6 +134,53 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- kind::f16 with bf16 operands (fp32 accumulate): the "bf16x3" products of the fused K-EDGE backward ------------
+// 16-bit operands use the plain SWIZZLE_128B layout for K-major AND MN-major reads, so ONE shared-memory tile
+// [row][64 bf16] serves a product that contracts over its columns (K-major) and one that contracts over its rows
+// (MN-major) -- verified on hardware by tools/umma_probe.cu (profiles/r2_a_umma_probe.txt).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// two fp32 -> packed bf16x2 (round to nearest even), low half = a
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// Two-term bf16 split of four fp32 values: hi = rn_bf16(v), lo = rn_bf16(v - hi); v - hi - lo is below 2^-17 |v| and of
+// either sign, so hi*hi + hi*lo + lo*hi reproduces an fp32 product to ~2^-16 with unbiased rounding.
+__device__ __forceinline__ void split_bf16x4(const float4& v, uint2& hi, uint2& lo) {
+  hi.x = pack_bf16x2(v.x, v.y);
+  hi.y = pack_bf16x2(v.z, v.w);
+  const float rx = v.x - __uint_as_float(hi.x << 16), ry = v.y - __uint_as_float(hi.x & 0xffff0000u);
+  const float rz = v.z - __uint_as_float(hi.y << 16), rw = v.w - __uint_as_float(hi.y & 0xffff0000u);
+  lo.x = pack_bf16x2(rx, ry);
+  lo.y = pack_bf16x2(rz, rw);
 }
 
 // Shared-memory matrix descriptor, sm_100 version field = 1

@@ -57,14 +57,14 @@ class GP2ConvFn(torch.autograd.Function):
                         L.ptr(wn), L.ptr(bnode), _bn_struct(gn, ben, rmn, rvn, nbtn))
         out = torch.empty(N, C_, dtype=torch.float32, device=x.device)
         xn_out = torch.empty(N, C_, dtype=torch.float32, device=x.device)
-        tape_n = lib.yolat_gp2_tape_floats(N, E, Cin, Cn, C_)
+        # bit 1 = forward only: no per-edge activation is written when autograd will not come back for it
+        mode = int(bool(training)) | (0 if (save_tape and any(ctx.needs_input_grad)) else 2)
+        tape_n = lib.yolat_gp2_tape_floats_mode(N, E, Cin, Cn, C_, mode)
         ws_n = lib.yolat_gp2_fwd_ws_floats(N, E, Cin, Cn, C_)
         if ws_n < 0:
             raise L.YolatError('attr_edge_gp2: out_channels must be 32, 64 or 128 (got %d)' % C_)
         tape = torch.empty(max(tape_n, 1), dtype=torch.float32, device=x.device)
         ws = L.workspace.get(ws_n, x.device)
-        # bit 1 = forward only: no per-edge activation is written when autograd will not come back for it
-        mode = int(bool(training)) | (0 if (save_tape and any(ctx.needs_input_grad)) else 2)
         L.check(lib.yolat_gp2_fwd(C.byref(P), Cin, Cn, C_, x.data_ptr(), x.stride(0), x_node.data_ptr(),
                                   x_node.stride(0), L.ptr(attr), L.ptr(ew), graph.ptr(), N, E, mode,
                                   out.data_ptr(), out.stride(0), xn_out.data_ptr(), xn_out.stride(0),
