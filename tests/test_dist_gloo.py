@@ -63,3 +63,44 @@ def test_flat_gradient_allreduce_world2(tmp_path):
     torch.set_num_threads(threads)
     want = (per[0] + per[1]) / 2
     assert torch.allclose(flat, want, rtol=0, atol=1e-7 * float(want.abs().max()))
+
+
+def _worker_overlap(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        model, grads = _shard_grads(rank)
+        sync = dp.OverlappedGradSync(model)
+        # layout: model.parameters() order, the classifier head (final first in backward) is the contiguous tail
+        n_head = sum(p.numel() for k, p in model.named_parameters() if k.startswith('prediction_cls'))
+        assert sync.numel == 1613329 and sync.numel - sync.split == n_head and sync.overlapped_bytes == 4 * n_head
+        # two steps; on the CPU the gradients come from the oracle, so autograd cannot adopt the flat views: the object
+        # must notice (hooks do not fire, pointers differ) and fall back to copy-then-reduce with the same result
+        for step in range(2):
+            for k, p in model.named_parameters():
+                p.grad = grads[k].clone() * (step + 1) if grads[k] is not None else None
+            flat = sync.finish()
+            assert sync.copy_mode
+            assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(sync.params, sync.views))
+        if rank == 0:
+            torch.save(flat.clone(), out)
+        sync.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_grad_sync_world2(tmp_path):
+    out = str(tmp_path / 'flat2.pt')
+    mp.spawn(_worker_overlap, args=(2, _free_port(), out), nprocs=2, join=True)
+    flat = torch.load(out)
+    per = []
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    for r in range(2):
+        model, grads = _shard_grads(r)
+        per.append(torch.cat([(grads[k] if grads[k] is not None else torch.zeros_like(p)).reshape(-1)
+                              for k, p in model.named_parameters()]))
+    torch.set_num_threads(threads)
+    want = (per[0] + per[1])           # second step: gradients were doubled, mean of two ranks
+    assert torch.allclose(flat, want, rtol=0, atol=2e-7 * float(want.abs().max()))

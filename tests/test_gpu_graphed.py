@@ -82,3 +82,69 @@ def test_packed_batch_prefetch_matches_plain_replay():
         g = model.prediction_cls[2][0].weight.grad
         gr = ref_model.prediction_cls[2][0].weight.grad
         assert float((g - gr).abs().max()) <= 1e-6 * float(gr.abs().max()) + 1e-12
+
+
+def test_captured_graphs_survive_workspace_growth():
+    """A graph captured for a small batch shape keeps replaying correctly after the shared scratch workspace has grown
+    (larger shapes, eval / predict passes) and after other tensors have been allocated: its workspace block is retired,
+    never freed (ADVICE r1 / VERDICT r1 weak #7).  Small / large / small / ... with bit-identical gradients on every
+    step against an eager model."""
+    from yolat_vectorgraphicsrecognition_b200 import _lib
+    from yolat_vectorgraphicsrecognition_b200.graphed import GraphedStep
+    synth, arch, opt, model = _setup()
+    ref_model = copy.deepcopy(model)
+    crit = arch.DetectionLoss(opt)
+    small = synth.floorplans_batch(graphs=1, n=320, e=1200, seed=5)
+    large = synth.floorplans_batch(graphs=4, n=2000, e=8000, seed=6)
+    huge = synth.floorplans_batch(graphs=8, n=4000, e=16000, seed=7)
+    step = GraphedStep(model, crit)
+    dev = next(model.parameters()).device
+    junk = []
+    for it, b in enumerate([small, large, small, huge, small, large, small]):
+        if it == 3:                       # an eager no-grad pass on an even larger shape grows the workspace again
+            with torch.no_grad():
+                model(huge, None)
+                ref_model(huge, None)
+        loss_g = step(b)
+        junk.append(torch.full((1 << 22,), float('nan'), device=dev))     # lands on any block the allocator got back
+        for p in ref_model.parameters():
+            p.grad = None
+        out = ref_model(b, None)
+        loss_e = crit(out, b)['loss']
+        loss_e.backward()
+        torch.cuda.synchronize()
+        assert float(loss_g.detach()) == float(loss_e.detach()), it
+        for (k, p), q in zip(model.named_parameters(), ref_model.parameters()):
+            assert torch.equal(p.grad, q.grad), (it, k)
+    assert len(step._graphs) == 3
+    assert _lib.workspace.retired_bytes(dev) > 0          # the smaller blocks are still owned
+
+
+def test_gradients_are_written_into_the_flat_buffer():
+    """dp.OverlappedGradSync: the backward kernels write every parameter gradient straight into views of one flat
+    buffer and autograd adopts them as p.grad (no gather copy before the all-reduce), eagerly and under graph replay;
+    values equal a plain run bit for bit."""
+    from yolat_vectorgraphicsrecognition_b200 import dp
+    from yolat_vectorgraphicsrecognition_b200.graphed import GraphedStep
+    synth, arch, opt, model = _setup()
+    ref_model = copy.deepcopy(model)
+    crit = arch.DetectionLoss(opt)
+    b = synth.floorplans_batch(graphs=1, n=640, e=2560, seed=1).to('cuda')
+    crit(ref_model(b, None), b)['loss'].backward()
+    sync = dp.OverlappedGradSync(model)
+    try:
+        crit(model(b, None), b)['loss'].backward()
+        flat = sync.finish()
+        assert not sync.copy_mode
+        lo, hi = flat.data_ptr(), flat.data_ptr() + 4 * flat.numel()
+        for (k, p), q in zip(model.named_parameters(), ref_model.parameters()):
+            assert lo <= p.grad.data_ptr() < hi, k
+            assert torch.equal(p.grad, q.grad), k
+        want = torch.cat([q.grad.reshape(-1) for q in ref_model.parameters()])
+        assert torch.equal(flat, want)
+        step = GraphedStep(model, crit, extra=sync.finish)
+        for _ in range(2):
+            step(b)
+        assert not sync.copy_mode and torch.equal(sync.flat, want)
+    finally:
+        sync.close()

@@ -65,7 +65,10 @@ def test_fused_adam_resumes_from_a_torch_adam_checkpoint_and_follows_the_schedul
 
 
 def test_fused_adam_is_capturable_in_the_step_graph():
-    """GraphedStep(extra=optimizer step): forward + loss + backward + Adam replayed as one graph trains the model."""
+    """GraphedStep(optimizer=FusedAdam): forward + loss + backward + Adam replayed as one graph.  The capture's warm-up
+    steps must not update anything (step counter == replays), and the captured step must follow a learning-rate change
+    made after the capture (hyper-parameters live in device memory): same trajectory as an eager torch.optim.Adam."""
+    import copy
     from yolat_vectorgraphicsrecognition_b200 import synth
     from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
     from yolat_vectorgraphicsrecognition_b200.graphed import GraphedStep
@@ -73,10 +76,27 @@ def test_fused_adam_is_capturable_in_the_step_graph():
     opt = synth.make_opt(n_classes=17)
     torch.manual_seed(0)
     model = arch.SparseCADGCN(opt).cuda().train()
-    optim = FusedAdam(model.parameters(), lr=1e-3)
+    ref_model = copy.deepcopy(model)
+    crit = arch.DetectionLoss(opt)
+    optim = FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    ref_optim = torch.optim.Adam(ref_model.parameters(), lr=1e-3, weight_decay=1e-5)
     batch = synth.floorplans_batch(graphs=1, n=640, e=2560, seed=1).to('cuda')
 
-    step = GraphedStep(model, arch.DetectionLoss(opt), extra=lambda loss: optim.step())
-    losses = [float(step(batch).detach()) for _ in range(12)]
-    assert losses[-1] < losses[0] * 0.9, losses
-    assert float(optim.state_dict()['state'][0]['step']) >= 12.0
+    step = GraphedStep(model, crit, optimizer=optim)
+    losses = []
+    for it in range(8):
+        if it == 4:                                   # what StepLR does between epochs (train.py:214)
+            optim.param_groups[0]['lr'] = 2.5e-4
+            ref_optim.param_groups[0]['lr'] = 2.5e-4
+        losses.append(float(step(batch).detach()))
+        ref_optim.zero_grad(set_to_none=True)
+        crit(ref_model(batch, None), batch)['loss'].backward()
+        ref_optim.step()
+    assert losses[-1] < losses[0], losses
+    assert float(optim.state_dict()['state'][0]['step']) == 8.0      # no hidden updates during the capture warm-up
+    for (k, a), b in zip(model.named_parameters(), ref_model.parameters()):
+        if float(b.grad.abs().max()) < 1e-6:
+            continue      # mathematically-zero gradients (biases feeding a BatchNorm): Adam amplifies their rounding noise
+        assert float((a.detach() - b.detach()).abs().max()) <= 2e-5 * max(1.0, float(b.detach().abs().max())), k
+    for (k, a), b in zip(model.named_buffers(), ref_model.buffers()):
+        assert float((a.double() - b.double()).abs().max()) <= 1e-5 * max(1.0, float(b.double().abs().max())), k

@@ -33,34 +33,50 @@ def _conv_pair(Cin, C, seed):
     return conv.cuda().train(), state
 
 
-def _check_conv(conv, state, x, xn, edge, attr, ew=None, fwd_tol=FWD_TOL, bwd_tol=BWD_TOL, seed=0):
-    """fwd + bwd of the CUDA conv against the fp64 restatement with the same upstream gradients."""
+def _ref_grads(state, x, xn, edge, attr, ew, go, gn, dtype):
     from oracle import restatement as R
+    st = R.clone_state({k: v.detach() for k, v in state.items()}, dtype)
+    xr = x.detach().to(dtype).clone().requires_grad_(True)
+    xnr = xn.detach().to(dtype).clone().requires_grad_(True)
+    out, on = R.gp2_conv(st, 'c.gconv', xr, xnr, edge.t(), attr.to(dtype), True,
+                         edge_weight=None if ew is None else ew.to(dtype))
+    params = {k: v for k, v in st.items() if v.requires_grad}
+    grads = torch.autograd.grad((out * go.to(dtype)).sum() + (on * gn.to(dtype)).sum(),
+                                [xr, xnr] + list(params.values()), allow_unused=True)
+    return out.detach(), on.detach(), params, grads
+
+
+def _check_conv(conv, state, x, xn, edge, attr, ew=None, fwd_tol=FWD_TOL, bwd_tol=BWD_TOL, seed=0, noise_floor=False):
+    """fwd + bwd of the CUDA conv against the fp64 restatement with the same upstream gradients.  noise_floor: at
+    millions of post-BN activations a handful sit within rounding distance of the ReLU boundary, so no fp32
+    implementation reproduces the fp64 gradients to 1e-4; the per-tensor bound is then
+    max(1e-4, 2 x the error of the fp32 RESTATEMENT against its own fp64 run), measured here on the same inputs."""
     g = torch.Generator().manual_seed(1000 + seed)
     N, C = x.shape[0], conv.gconv.lin_r.weight.shape[0]
     go, gn = torch.randn(N, C, generator=g), torch.randn(N, C, generator=g)
-    x64 = x.double().requires_grad_(True)
-    xn64 = xn.double().requires_grad_(True)
-    out64, on64 = R.gp2_conv(state, 'c.gconv', x64, xn64, edge.t(), attr.double(), True,
-                             edge_weight=None if ew is None else ew.double())
-    params = {k: v for k, v in state.items() if v.requires_grad}
-    grads = torch.autograd.grad((out64 * go.double()).sum() + (on64 * gn.double()).sum(),
-                                [x64, xn64] + list(params.values()), allow_unused=True)
-    xc = x.cuda().requires_grad_(True)
-    xnc = xn.cuda().requires_grad_(True)
+    out64, on64, params, grads = _ref_grads(state, x, xn, edge, attr, ew, go, gn, torch.float64)
+    noise = None
+    if noise_floor:
+        _, _, _, g32 = _ref_grads(state, x, xn, edge, attr, ew, go, gn, torch.float32)
+        noise = [0.0 if a is None else l2_rel(a, b) for a, b in zip(g32, grads)]
+
+    def tol(i):
+        return bwd_tol if noise is None else max(bwd_tol, 2.0 * noise[i])
+    xc = x.detach().cuda().requires_grad_(True)
+    xnc = xn.detach().cuda().requires_grad_(True)
     out, on = conv(xc, edge.t().cuda(), None if ew is None else ew.cuda(), attr.cuda(), x_node=xnc)
     assert max_rel(out, out64) < fwd_tol, ('out', max_rel(out, out64))
     assert max_rel(on, on64) < fwd_tol, ('xnode', max_rel(on, on64))
     ((out * go.cuda()).sum() + (on * gn.cuda()).sum()).backward()
-    assert l2_rel(xc.grad, grads[0]) < bwd_tol, ('dx', l2_rel(xc.grad, grads[0]))
-    assert l2_rel(xnc.grad, grads[1]) < bwd_tol, ('dxnode', l2_rel(xnc.grad, grads[1]))
+    assert l2_rel(xc.grad, grads[0]) < tol(0), ('dx', l2_rel(xc.grad, grads[0]), tol(0))
+    assert l2_rel(xnc.grad, grads[1]) < tol(1), ('dxnode', l2_rel(xnc.grad, grads[1]), tol(1))
     got = dict(conv.named_parameters())
-    for (k, _), ref in zip(params.items(), grads[2:]):
+    for i, ((k, _), ref) in enumerate(zip(params.items(), grads[2:])):
         p = got[k[2:]]
         if ref is None or float(ref.abs().max()) < 1e-9 * max(1.0, float(go.abs().max())):
             assert float(p.grad.abs().max()) < 2e-5 * (1 + N / 1000.0), k      # bias feeding a training-mode BN
         else:
-            assert l2_rel(p.grad, ref) < bwd_tol, (k, l2_rel(p.grad, ref))
+            assert l2_rel(p.grad, ref) < tol(2 + i), (k, l2_rel(p.grad, ref), tol(2 + i))
 
 
 @pytest.mark.parametrize('config', ['floorplans', 'diagrams'])
@@ -78,19 +94,21 @@ def test_model_matches_oracle_full_config(config):
     batch = make()
     assert batch.x.shape[0] == (20000 if config == 'floorplans' else 12000)
     ref = R.run_step(st, opt, batch, training=True)
+    ref32 = R.run_step(R.clone_state(model.state_dict(), torch.float32), opt, batch, training=True)
     model = model.cuda().train()
     out = model(batch, None)
     loss = arch.DetectionLoss(opt)(out, batch)['loss']
     loss.backward()
     assert max_rel(out[0], ref['logits']) < FWD_TOL, max_rel(out[0], ref['logits'])
-    assert abs(float(loss) - float(ref['loss'])) < FWD_TOL
+    assert abs(float(loss.detach()) - float(ref['loss'])) < FWD_TOL
     for k, p in model.named_parameters():
         g = ref['grads'][k]
         if float(g.abs().max()) < 1e-12:
             assert float(p.grad.abs().max()) < 2e-5, k
-        else:
+        else:   # bound: twice the restatement's own fp32-vs-fp64 error on this tensor, measured here
             rel = float((p.grad.double().cpu() - g).norm() / g.norm())
-            assert rel < 5e-3, (k, rel)
+            noise = float((ref32['grads'][k].double() - g).norm() / g.norm())
+            assert rel < max(1e-4, 2.0 * noise) * 1.5, (k, rel, noise)
     for k, v in st.items():
         if 'running' in k:
             assert max_rel(model.state_dict()[k], v) < FWD_TOL, k
@@ -105,7 +123,7 @@ def test_gp2conv_roofline_shape_vs_oracle():
     g = torch.Generator().manual_seed(5)
     x = torch.randn(b.x.shape[0], 64, generator=g)
     xn = torch.randn(b.x.shape[0], 64, generator=g)
-    _check_conv(conv, state, x, xn, b.edge, b.e_attr, seed=1)
+    _check_conv(conv, state, x, xn, b.edge, b.e_attr, seed=1, noise_floor=True)
 
 
 @pytest.mark.parametrize('C', [32, 128])
@@ -127,10 +145,10 @@ def test_gp2conv_hierarchical_union_graph():
     N = b.x.shape[0]
     g = torch.Generator().manual_seed(9)
     conv, state = _conv_pair(5, 64, 21)
-    _check_conv(conv, state, b.x, b.x, b.edge, b.e_attr, seed=2)
+    _check_conv(conv, state, b.x, b.x, b.edge, b.e_attr, seed=2, noise_floor=True)
     conv, state = _conv_pair(64, 64, 22)
     _check_conv(conv, state, torch.randn(N, 64, generator=g), torch.randn(N, 64, generator=g), b.edge, b.e_attr,
-                ew=torch.rand(b.edge.shape[0], generator=g), seed=3)
+                ew=torch.rand(b.edge.shape[0], generator=g), seed=3, noise_floor=True)
 
 
 def test_gp2conv_zero_edges_training():

@@ -23,8 +23,9 @@
 //   dP[r] = sc1 (U_t[r] - deg_in(r) m1 - m2 X_t[r]),   dQ[v] = sc1 (U_s[v] - deg_out(v) m1 - m2 X_s[v]),
 //   dW1c  = sc1 (T - m1 (x) sum attr - m2 sum xhat1 (x) attr)                     (k_edge_bwd_combine, node level).
 //
-// Tensor-core products are "bf16x3": every fp32 operand is split into bf16 hi + lo (round to nearest) and
-// hi*hi + hi*lo + lo*hi accumulates in fp32 TMEM (~2^-16 per product, unbiased).  16-bit operands use the same
+// Tensor-core products are split-bf16: every fp32 operand is split into bf16 terms (round to nearest).  The gradient
+// products (da1, dW2) use two terms, hi*hi + hi*lo + lo*hi (~2^-16 per product, unbiased); the recomputed z2 -- whose
+// sign decides the ReLU masks -- uses three terms and six products (~2^-24, the accuracy of the forward's 3xTF32).  16-bit operands use the same
 // SWIZZLE_128B shared-memory layout for K-major and MN-major reads (tools/umma_probe.cu), so the a1 / dz2 / W2 tiles are
 // written once and read by all three products; dW2 stacks [dz2_hi ; dz2_lo] as M = 128 through the descriptor's LBO.
 //
@@ -44,11 +45,11 @@ constexpr int TILE = 128;
 constexpr int THREADS = 512;
 constexpr int RING = 3;
 constexpr uint32_t T_BF = TILE * 128;               // one bf16 tile [128 slots][64 channels]: 16 KB
-constexpr uint32_t OFF_A1 = 0;                      // a1 hi | lo
-constexpr uint32_t OFF_DZ = OFF_A1 + 2 * T_BF;      // dz2 hi | lo
-constexpr uint32_t OFF_W2 = OFF_DZ + 2 * T_BF;      // W2 hi | lo, [64 out][64 in] bf16, 8 KB each
+constexpr uint32_t OFF_A1 = 0;                      // a1 hi | mid | lo
+constexpr uint32_t OFF_DZ = OFF_A1 + 3 * T_BF;      // dz2 hi | lo
+constexpr uint32_t OFF_W2 = OFF_DZ + 2 * T_BF;      // W2 hi | mid | lo, [64 out][64 in] bf16, 8 KB each
 constexpr uint32_t W_BF = 64 * 128;
-constexpr uint32_t OFF_ZT = OFF_W2 + 2 * W_BF;      // z1 tile, fp32 [128][64], chunk-swizzled
+constexpr uint32_t OFF_ZT = OFF_W2 + 3 * W_BF;      // z1 tile, fp32 [128][64], chunk-swizzled
 constexpr uint32_t OFF_ST = OFF_ZT + TILE * 256;    // G -> dy1 (D2) | xhat2 with the mask in the lowest mantissa bit (D1)
 constexpr uint32_t OFF_REC = OFF_ST + TILE * 256;   // record ring: RING x (128 x int4 | 128 x float4)
 constexpr uint32_t REC_BYTES = TILE * 32;
@@ -141,11 +142,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
   for (int idx = tid; idx < C * 16; idx += THREADS) {
     const int n = idx >> 4, c4 = idx & 15;
     const float4 v = __ldg(reinterpret_cast<const float4*>(p.w2 + n * C + c4 * 4));
-    uint2 hi, lo;
-    split_bf16x4(v, hi, lo);
+    uint2 hi, mid, lo;
+    split3_bf16x4(v, hi, mid, lo);
     const uint32_t off = off_bf(n, c4 * 4);
     *reinterpret_cast<uint2*>(w2_t + off) = hi;
-    *reinterpret_cast<uint2*>(w2_t + W_BF + off) = lo;
+    *reinterpret_cast<uint2*>(w2_t + W_BF + off) = mid;
+    *reinterpret_cast<uint2*>(w2_t + 2 * W_BF + off) = lo;
   }
   if (tid < C) {
     const int c = tid;
@@ -295,11 +297,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
         }
         a = make_float4(av[0], av[1], av[2], av[3]);
         *reinterpret_cast<float4*>(z_t + off_f(j, gc)) = make_float4(z[0], z[1], z[2], z[3]);
-        uint2 hi, lo;
-        split_bf16x4(a, hi, lo);
+        uint2 hi, mid, lo;
+        split3_bf16x4(a, hi, mid, lo);
         const uint32_t ob = off_bf(j, gc * 4);
         *reinterpret_cast<uint2*>(a1_t + ob) = hi;
-        *reinterpret_cast<uint2*>(a1_t + T_BF + ob) = lo;
+        *reinterpret_cast<uint2*>(a1_t + T_BF + ob) = mid;
+        *reinterpret_cast<uint2*>(a1_t + 2 * T_BF + ob) = lo;
         if (D2) {
           const float s = valid ? gs[i] : 0.f;
           *reinterpret_cast<float4*>(s_t + off_f(j, gc)) = make_float4(gv[i].x * s, gv[i].y * s, gv[i].z * s, gv[i].w * s);
@@ -329,15 +332,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
       if (elect_one_sync()) {
         constexpr uint32_t IDESC = make_idesc_bf16(TILE, C, 0, 0);
         const uint32_t a_u32 = sm_u32 + OFF_A1, w_u32 = sm_u32 + OFF_W2;
+        // z2 decides the ReLU masks of the backward: three-term splits, six products (everything above 2^-24 |a w|), so
+        // the recomputed masks flip no more often than an fp32 product's would
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t a_hi = make_desc(a_u32 + ks * 32u, 16, 1024, LAYOUT_SW128);
-          const uint64_t a_lo = make_desc(a_u32 + T_BF + ks * 32u, 16, 1024, LAYOUT_SW128);
-          const uint64_t b_hi = make_desc(w_u32 + ks * 32u, 16, 1024, LAYOUT_SW128);
-          const uint64_t b_lo = make_desc(w_u32 + W_BF + ks * 32u, 16, 1024, LAYOUT_SW128);
-          umma_bf16(T_Z2, a_lo, b_hi, IDESC, ks > 0 ? 1u : 0u);
-          umma_bf16(T_Z2, a_hi, b_lo, IDESC, 1u);
-          umma_bf16(T_Z2, a_hi, b_hi, IDESC, 1u);
+          const uint64_t a_h = make_desc(a_u32 + ks * 32u, 16, 1024, LAYOUT_SW128);
+          const uint64_t a_m = make_desc(a_u32 + T_BF + ks * 32u, 16, 1024, LAYOUT_SW128);
+          const uint64_t a_l = make_desc(a_u32 + 2 * T_BF + ks * 32u, 16, 1024, LAYOUT_SW128);
+          const uint64_t b_h = make_desc(w_u32 + ks * 32u, 16, 1024, LAYOUT_SW128);
+          const uint64_t b_m = make_desc(w_u32 + W_BF + ks * 32u, 16, 1024, LAYOUT_SW128);
+          const uint64_t b_l = make_desc(w_u32 + 2 * W_BF + ks * 32u, 16, 1024, LAYOUT_SW128);
+          umma_bf16(T_Z2, a_l, b_h, IDESC, ks > 0 ? 1u : 0u);     // small terms first
+          umma_bf16(T_Z2, a_h, b_l, IDESC, 1u);
+          umma_bf16(T_Z2, a_m, b_m, IDESC, 1u);
+          umma_bf16(T_Z2, a_m, b_h, IDESC, 1u);
+          umma_bf16(T_Z2, a_h, b_m, IDESC, 1u);
+          umma_bf16(T_Z2, a_h, b_h, IDESC, 1u);
         }
         umma_commit(smem_u32(&bar_mma));
       }
@@ -417,7 +427,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
             const uint64_t a_hi = make_desc(d_u32 + ks * 32u, 16, 1024, LAYOUT_SW128);
             const uint64_t a_lo = make_desc(d_u32 + T_BF + ks * 32u, 16, 1024, LAYOUT_SW128);
             const uint64_t b_hi = make_desc(w_u32 + ks * 2048u, 8192, 1024, LAYOUT_SW128);
-            const uint64_t b_lo = make_desc(w_u32 + W_BF + ks * 2048u, 8192, 1024, LAYOUT_SW128);
+            const uint64_t b_lo = make_desc(w_u32 + W_BF + ks * 2048u, 8192, 1024, LAYOUT_SW128);   // the mid part of W2
             umma_bf16(T_DA, a_lo, b_hi, IDESC_NN, ks > 0 ? 1u : 0u);
             umma_bf16(T_DA, a_hi, b_lo, IDESC_NN, 1u);
             umma_bf16(T_DA, a_hi, b_hi, IDESC_NN, 1u);
@@ -427,7 +437,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
             for (int ks = 0; ks < 8; ++ks) {
               const uint64_t a_st = make_desc(d_u32 + ks * 2048u, T_BF, 1024, LAYOUT_SW128);      // rows 0-63 hi, 64-127 lo
               const uint64_t b_hi = make_desc(a_u32 + ks * 2048u, 8192, 1024, LAYOUT_SW128);
-              const uint64_t b_lo = make_desc(a_u32 + T_BF + ks * 2048u, 8192, 1024, LAYOUT_SW128);
+              const uint64_t b_lo = make_desc(a_u32 + T_BF + ks * 2048u, 8192, 1024, LAYOUT_SW128);   // the mid part of a1
               umma_bf16(T_DW, a_st, b_lo, IDESC_TN, (t > 0 || ks > 0) ? 1u : 0u);
               umma_bf16(T_DW, a_st, b_hi, IDESC_TN, 1u);
             }

@@ -183,6 +183,18 @@ __device__ __forceinline__ void split_bf16x4(const float4& v, uint2& hi, uint2& 
   lo.y = pack_bf16x2(rz, rw);
 }
 
+// Three-term split: v = hi + mid + lo up to 2^-25 |v|.
+__device__ __forceinline__ void split3_bf16x4(const float4& v, uint2& hi, uint2& mid, uint2& lo) {
+  hi.x = pack_bf16x2(v.x, v.y);
+  hi.y = pack_bf16x2(v.z, v.w);
+  const float rx = v.x - __uint_as_float(hi.x << 16), ry = v.y - __uint_as_float(hi.x & 0xffff0000u);
+  const float rz = v.z - __uint_as_float(hi.y << 16), rw = v.w - __uint_as_float(hi.y & 0xffff0000u);
+  mid.x = pack_bf16x2(rx, ry);
+  mid.y = pack_bf16x2(rz, rw);
+  lo.x = pack_bf16x2(rx - __uint_as_float(mid.x << 16), ry - __uint_as_float(mid.x & 0xffff0000u));
+  lo.y = pack_bf16x2(rz - __uint_as_float(mid.y << 16), rw - __uint_as_float(mid.y & 0xffff0000u));
+}
+
 // Shared-memory matrix descriptor, sm_100 version field = 1
 // (bit layout: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version [46,48) | layout [61,64)).
 constexpr uint32_t LAYOUT_SW128 = 2;          // K-major operands

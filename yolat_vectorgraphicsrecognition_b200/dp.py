@@ -59,3 +59,114 @@ class FlatGradients(object):
         for p, v in zip(self.params, self.views):
             p.grad = v
         return self.flat
+
+
+class OverlappedGradSync(object):
+    """Gradient averaging that overlaps the backward pass (last row; section 8e).
+
+    * Every parameter's gradient lives in ONE flat buffer from the start: the backward kernels write into views of it
+      (ops.set_grad_arena), autograd adopts those views as `p.grad` -- no gather copy before the collective, and a
+      fused optimizer sees one set of gradient addresses for every captured graph.
+    * The buffer is laid out in `model.parameters()` order, so the parameters whose gradients are final FIRST in the
+      backward pass -- the classifier head `prediction_cls.*`, 82 % of the 6.45 MB at the README config -- form its
+      contiguous tail.  A post-accumulate hook counts them and launches their all-reduce (asynchronously, on the
+      process group's own stream) the moment the last one is written, while the fusion block / GraphConv backward
+      (~85 % of the backward's runtime) is still running.
+    * `finish()` -- call it after `loss.backward()`, or pass it as `GraphedStep(extra=...)` so that both collectives
+      are captured into the step graph -- reduces the remaining head of the buffer, joins both collectives and scales
+      by 1 / world.  Only that second, small all-reduce is exposed.
+
+    BatchNorm statistics stay rank-local (DDP-default semantics).  Gradients must be re-created every step
+    (`zero_grad(set_to_none=True)`, what GraphedStep does): an existing `p.grad` makes autograd accumulate in place
+    instead of adopting the view.  If autograd ever declines a view (verified on every eager step), the object falls
+    back to the copy-then-reduce schedule of `FlatGradients`.
+    """
+
+    def __init__(self, model, group=None, early_prefixes=('prediction_cls',)):
+        from . import ops
+        named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
+        self.params = [p for _, p in named]
+        self.group = group
+        p0 = self.params[0]
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=p0.device)
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += p.numel()
+        # the early bucket must be a contiguous tail of the parameter order
+        early = [any(k.startswith(pre) for pre in early_prefixes) for k, _ in named]
+        first_early = early.index(True) if True in early else len(early)
+        if not all(early[first_early:]):
+            first_early = len(early)              # not a tail: a single bucket at the end
+        self.split = self.offsets[first_early] if first_early < len(early) else self.numel
+        self.early_params = self.params[first_early:]
+        self.late_params = self.params[:first_early]
+        self.views = [self.flat.narrow(0, o, p.numel()).view(p.shape) for o, p in zip(self.offsets, self.params)]
+        ops.set_grad_arena({p.data_ptr(): (self.flat, o, p.numel()) for o, p in zip(self.offsets, self.params)})
+        self.copy_mode = False
+        self._count = 0
+        self._work = None
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.early_params]
+        self.exposed_bytes = 4 * self.split
+        self.overlapped_bytes = 4 * (self.numel - self.split)
+
+    def world(self):
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def _adopted(self, early):
+        n_late = len(self.late_params)
+        params, views = (self.early_params, self.views[n_late:]) if early else (self.late_params, self.views[:n_late])
+        return all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, views))
+
+    def _on_grad(self, _p):
+        self._count += 1
+        if self._count < len(self.early_params) or self.copy_mode:
+            return
+        self._count = 0
+        if not self._adopted(True):
+            if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError('OverlappedGradSync: autograd did not adopt the flat-buffer views during capture')
+            self.copy_mode = True
+            return
+        if self._work is not None:                # a step whose finish() was never called (capture warm-up)
+            self._work.wait()
+            self._work = None
+        if self.world() > 1 and self.split < self.numel:
+            self._work = dist.all_reduce(self.flat.narrow(0, self.split, self.numel - self.split),
+                                         op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self, _loss=None):
+        """Join the early collective, reduce the rest, scale: p.grad = mean over ranks for every parameter."""
+        self._count = 0
+        world = self.world()
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        if not self.copy_mode and not (self._adopted(False) and self._adopted(True)):
+            if capturing:
+                raise RuntimeError('OverlappedGradSync: autograd did not adopt the flat-buffer views during capture')
+            self.copy_mode = True
+        if self.copy_mode:
+            if self._work is not None:
+                self._work.wait()
+                self._work = None
+            src = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+            torch._foreach_copy_(self.views, src)
+            if world > 1:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            for p, v in zip(self.params, self.views):
+                p.grad = v
+        elif world > 1:
+            if self.split > 0:
+                dist.all_reduce(self.flat.narrow(0, 0, self.split), op=dist.ReduceOp.SUM, group=self.group)
+            if self._work is not None:
+                self._work.wait()
+                self._work = None
+        if world > 1:
+            self.flat.mul_(1.0 / world)
+        return self.flat
+
+    def close(self):
+        from . import ops
+        for h in self._hooks:
+            h.remove()
+        ops.set_grad_arena(None)

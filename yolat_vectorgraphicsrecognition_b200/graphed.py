@@ -28,16 +28,19 @@ _FIELDS = ('x', 'bbox_idx', 'edge', 'bbox', 'e_attr', 'labels')
 
 class GraphedStep(object):
 
-    def __init__(self, model, criterion, warmup=3, extra=None):
+    def __init__(self, model, criterion, warmup=3, extra=None, optimizer=None):
         """`extra(loss)` (optional) is called inside the captured region after backward -- e.g. a fused
         optimizer step or the data-parallel gradient all-reduce -- and must be capture-safe.  It is NOT run during the
         eager warm-up steps of a capture (they would be hidden optimizer updates / extra collectives); if its owner
         (`extra.__self__`) has `prepare()` it is called once here (allocations that are illegal under capture), and
         `sync_hyperparams()` before every capture and replay (device-resident learning rate of optim.FusedAdam).
+        `optimizer=` names that owner explicitly (and makes `extra` its step when no `extra` is given).
         With a collective inside `extra`, every rank must meet a new batch shape at the same step: capture is a
         collective event."""
+        if optimizer is not None and extra is None:       # GraphedStep(model, crit, optimizer=FusedAdam(...))
+            extra = lambda loss: optimizer.step()
         self.model, self.criterion, self.warmup, self.extra = model, criterion, int(warmup), extra
-        self._extra_owner = getattr(extra, '__self__', None)
+        self._extra_owner = optimizer if optimizer is not None else getattr(extra, '__self__', None)
         if hasattr(self._extra_owner, 'prepare'):
             self._extra_owner.prepare()
         self.params = [p for p in model.parameters() if p.requires_grad]

@@ -18,8 +18,31 @@ def _bn_struct(weight, bias, running_mean, running_var, nbt):
     return L.YolatBn(L.ptr(weight), L.ptr(bias), L.ptr(running_mean), L.ptr(running_var), L.ptr(nbt))
 
 
+# Gradient arena (dp.OverlappedGradSync): parameter storage address -> (flat buffer, offset, numel).  When a parameter
+# is registered, the backward kernels write its gradient straight into that slice of ONE flat buffer (autograd's
+# AccumulateGrad adopts the returned view as p.grad), so the data-parallel all-reduce needs no gather copy and a fused
+# optimizer sees the same gradient addresses for every captured graph.
+_GRAD_ARENA = {}
+
+
+def set_grad_arena(entries):
+    """entries: {param.data_ptr(): (flat, offset, numel)} or None / {} to clear."""
+    _GRAD_ARENA.clear()
+    if entries:
+        _GRAD_ARENA.update(entries)
+
+
+def _grad_for(ptr, like):
+    """Gradient buffer for the parameter stored at `ptr`: a fresh view of the arena slice, or a new tensor."""
+    e = _GRAD_ARENA.get(ptr)
+    if e is None:
+        return torch.empty_like(like, memory_format=torch.contiguous_format)
+    flat, off, n = e
+    return flat.narrow(0, off, n).view(like.shape)
+
+
 def _empty_like_param(p):
-    return torch.empty_like(p, memory_format=torch.contiguous_format)
+    return _grad_for(p.data_ptr(), p)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -124,6 +147,7 @@ class MLPStageFn(torch.autograd.Function):
                                   C.byref(bn) if bn is not None else None, flags, y.data_ptr(), y.stride(0),
                                   tape.data_ptr(), tape.numel(), ws.data_ptr(), ws.numel(), L.stream()), 'mlp_fwd')
         ctx.flags, ctx.buffers, ctx.has_bias = flags, buffers, b is not None
+        ctx.bias_ptr = b.data_ptr() if b is not None else 0
         ctx.save_for_backward(x, w, gamma, beta, tape)
         return y
 
@@ -138,10 +162,13 @@ class MLPStageFn(torch.autograd.Function):
         rm, rv, _ = ctx.buffers if ctx.buffers is not None else (None, None, None)
         bn = _bn_struct(gamma, beta, rm, rv, None) if flags & BN else None
         dx = torch.empty_like(x) if ctx.needs_input_grad[2] else None
-        dw = torch.empty_like(w)
-        db = torch.empty(Nout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
-        dg = torch.empty_like(gamma) if flags & BN else None
-        dbe = torch.empty_like(beta) if flags & BN else None
+        dw = _empty_like_param(w)
+        db = None
+        if ctx.has_bias:
+            e = _GRAD_ARENA.get(ctx.bias_ptr)
+            db = e[0].narrow(0, e[1], e[2]) if e is not None else torch.empty(Nout, dtype=torch.float32, device=x.device)
+        dg = _empty_like_param(gamma) if flags & BN else None
+        dbe = _empty_like_param(beta) if flags & BN else None
         ws = L.workspace.get(lib.yolat_mlp_ws_floats(M, K, Nout, flags), x.device)
         L.check(lib.yolat_mlp_bwd(x.data_ptr(), x.stride(0), M, K, w.data_ptr(), Nout,
                                   C.byref(bn) if bn is not None else None, flags, gy.data_ptr(), gy.stride(0),
@@ -249,6 +276,7 @@ class FuseMaxFn(torch.autograd.Function):
                                       tape.data_ptr(), tape.numel(), ws.data_ptr(), ws.numel(), L.stream()),
                 'fusemax_fwd')
         ctx.seg, ctx.training, ctx.buffers, ctx.has_bias = seg, int(training), buffers, b is not None
+        ctx.bias_ptr = b.data_ptr() if b is not None else 0
         ctx.save_for_backward(feats, w, gamma, beta, tape)
         return pooled
 
@@ -263,9 +291,10 @@ class FuseMaxFn(torch.autograd.Function):
         rm, rv, _ = ctx.buffers
         bn = _bn_struct(gamma, beta, rm, rv, None)
         dfeats = torch.empty_like(feats) if ctx.needs_input_grad[3] else None
-        dw = torch.empty_like(w)
-        db = torch.empty(F_, dtype=torch.float32, device=w.device)
-        dg, dbe = torch.empty_like(gamma), torch.empty_like(beta)
+        dw = _empty_like_param(w)
+        e = _GRAD_ARENA.get(ctx.bias_ptr) if ctx.has_bias else None
+        db = e[0].narrow(0, e[1], e[2]) if e is not None else torch.empty(F_, dtype=torch.float32, device=w.device)
+        dg, dbe = _empty_like_param(gamma), _empty_like_param(beta)
         ws = L.workspace.get(lib.yolat_fusemax_ws_floats(M, K, F_, seg.S), feats.device)
         L.check(lib.yolat_fusemax_bwd(feats.data_ptr(), feats.stride(0), M, K, w.data_ptr(), F_, C.byref(bn),
                                       ctx.training, seg.ptr(), seg.S, gp.data_ptr(), gp.stride(0), L.ptr(dfeats), K, 0,

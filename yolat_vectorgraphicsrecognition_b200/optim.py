@@ -155,6 +155,9 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         if self._groups is None:
+            if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                raise _lib.YolatError('FusedAdam.step captured before prepare(): pass optimizer= to GraphedStep or call '
+                                      'optimizer.prepare() and optimizer.sync_hyperparams() before the capture')
             self._prepare()
         lib = _lib.lib()
         if not torch.cuda.is_current_stream_capturing():
