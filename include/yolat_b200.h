@@ -246,6 +246,14 @@ int yolat_slice_graph(const int64_t* pos_idx, int64_t Np, const int64_t* edge_id
                       int64_t E_all, int64_t N_all, const int64_t* bbox_idx, int32_t* ws, int64_t* edge_out,
                       int64_t* bbox_idx_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Per-image index offsets of a collated batch (cad_recognition/train.py:238-258: python loop over the batch items on
+ * host tensors).  edge [E,2] += node offset of the edge's image, bbox_idx [N] += proposal offset of the node's image,
+ * in place, one launch.  tab: [4][G+1] int64 prefix sums (device): edge slices | pos slices | bbox_idx slices |
+ * labels slices, as train.collate returns them in `slices` (train.py:123-171).
+ * ---------------------------------------------------------------------------------------------- */
+int yolat_batch_offsets(int64_t* edge, int64_t E, int64_t* bbox_idx, int64_t N, const int64_t* tab, int64_t G, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

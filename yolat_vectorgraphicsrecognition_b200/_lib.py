@@ -77,6 +77,7 @@ _SIGS = {
     'yolat_expand_ranges': (C.c_int, [vp, vp, i64, i64, vp, vp]),
     'yolat_slice_graph_ints': (i64, [i64, i64]),
     'yolat_slice_graph': (C.c_int, [vp, i64, vp, i64, vp, i64, i64, vp, vp, vp, vp, vp]),
+    'yolat_batch_offsets': (C.c_int, [vp, i64, vp, i64, vp, i64, vp]),
     'yolat_adam_chunk': (C.c_int, []),
     'yolat_adam_step': (C.c_int, [vp, vp, i64, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_double, vp]),

@@ -20,6 +20,19 @@ from .graph import CSRGraph, Segments
 from .torch_scatter import scatter
 
 
+def _packed_to_device(data, device):
+    """A batch.PackedBatch reaches the device as ONE copy of its pinned buffer; per-image offsets deferred by
+    `batch.collate(...).defer_offsets()` (train.py:238-258) are applied there.  The device views are remembered on the
+    batch so that DetectionLoss finds the labels without a second upload."""
+    from .batch import apply_offsets
+    buf, ns = data.device_twin(device)
+    buf.copy_(data.host, non_blocking=True)
+    if getattr(data, 'offsets_pending', False):
+        apply_offsets(ns)
+    data._device = ns
+    return ns
+
+
 def _dev(t, device):
     """`.cuda()` of the reference (:107-115), a no-op for tensors that already live on the device."""
     return t if t.is_cuda else t.to(device, non_blocking=True)
@@ -131,6 +144,8 @@ class SparseCADGCN(torch.nn.Module):
         """:106-137.  `data` carries x [N,Cin], bbox_idx [N], edge [E,2], bbox [B,4], stat_feats, e_attr [E,4]
         as CPU or CUDA tensors; returns (pred_cls [B,ncls], pred_bbox [B,4])."""
         dev = self._device()
+        if hasattr(data, 'device_twin') and hasattr(data, 'host'):      # batch.PackedBatch
+            data = _packed_to_device(data, dev)
         x = _dev(data.x, dev)
         bbox_idx = _dev(data.bbox_idx, dev)
         edge = _dev(data.edge, dev)
@@ -272,7 +287,7 @@ class DetectionLoss(torch.nn.Module):
 
     def forward(self, out, data):
         pred_cls = out[0]
-        gt_cls = _dev(data.labels, pred_cls.device)
+        gt_cls = _dev(getattr(data, '_device', data).labels, pred_cls.device)
         if self.classifier == 'softmax':
             l0 = ops.softmax_cross_entropy(pred_cls, gt_cls)      # CrossEntropyLoss(mean), :363,376
         else:

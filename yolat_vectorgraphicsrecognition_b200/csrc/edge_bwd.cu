@@ -53,8 +53,8 @@ constexpr uint32_t OFF_ZT = OFF_W2 + 3 * W_BF;      // z1 tile, fp32 [128][64], 
 constexpr uint32_t OFF_ST = OFF_ZT + TILE * 256;    // G -> dy1 (D2) | xhat2 with the mask in the lowest mantissa bit (D1)
 constexpr uint32_t OFF_REC = OFF_ST + TILE * 256;   // record ring: RING x (128 x int4 | 128 x float4)
 constexpr uint32_t REC_BYTES = TILE * 32;
-constexpr uint32_t OFF_TAB = OFF_REC + RING * REC_BYTES;   // per-channel tables, 12 x 64 floats
-constexpr uint32_t OFF_EW = OFF_TAB + 12 * 256;     // edge weight per slot (D1)
+constexpr uint32_t OFF_TAB = OFF_REC + RING * REC_BYTES;   // per-channel tables, 16 x 64 floats
+constexpr uint32_t OFF_EW = OFF_TAB + 16 * 256;     // edge weight per slot (D1)
 constexpr uint32_t OFF_CARRY = OFF_EW + TILE * 4;   // [2 parities][U | X][64]
 constexpr uint32_t SMEM_BYTES = OFF_CARRY + 2 * 2 * 256 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -62,7 +62,7 @@ static_assert(OFF_REC >= 64 * 8 * 48 * 4 && OFF_REC >= (64 * 8 * 16 + 32 * 16 * 
 
 enum { M_D1 = 0, M_D2T = 1, M_D2S = 2 };
 // per-channel tables
-enum { TB_SC1 = 0, TB_SH1, TB_IS1, TB_XM1, TB_SC2, TB_SH2B, TB_IS2, TB_XM2, TB_C0, TB_C1 };
+enum { TB_SC1 = 0, TB_SH1, TB_IS1, TB_XM1, TB_SC2, TB_SH2B, TB_IS2, TB_XM2, TB_C0, TB_C1, TB_B1, TB_W1C /* 4 rows: k */ };
 
 struct Params {
   const int32_t* rowptr;      // [N + 1] of this pass's slot order
@@ -155,6 +155,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
     const float sc2 = __ldg(p.stat2 + c), sh2 = __ldg(p.stat2 + C + c), mu2 = __ldg(p.stat2 + 2 * C + c), is2 = __ldg(p.stat2 + 3 * C + c);
     const float b2 = p.b2 ? __ldg(p.b2 + c) : 0.f;
     tab[TB_SC1 * C + c] = sc1; tab[TB_SH1 * C + c] = sh1; tab[TB_IS1 * C + c] = is1; tab[TB_XM1 * C + c] = -mu1 * is1;
+    tab[TB_B1 * C + c] = p.b1 ? __ldg(p.b1 + c) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tab[(TB_W1C + k) * C + c] = __ldg(p.w1c + c * p.ld1 + k);
     tab[TB_SC2 * C + c] = sc2; tab[TB_SH2B * C + c] = fmaf(b2, sc2, sh2);
     const float xm2 = (b2 - mu2) * is2;
     tab[TB_IS2 * C + c] = is2; tab[TB_XM2 * C + c] = xm2;
@@ -193,29 +196,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
   };
   if (tid == 0) { fill(0); fill(1); }
 
-  // ---- gather-phase constants: thread (gc, sl) = channels 4 gc .. 4 gc + 3 of slots sl + 32 i ----
+  // ---- gather mapping: thread (gc, sl) = channels 4 gc .. 4 gc + 3 of slots sl + 32 i (constants come from the tables) ----
   const int gc = tid & 15, sl = tid >> 4;
-  float w1c[4][4], b1v[4], sc1v[4], sh1v[4], is1v[4], xm1v[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int c = gc * 4 + q;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) w1c[q][k] = __ldg(p.w1c + c * p.ld1 + k);
-    b1v[q] = p.b1 ? __ldg(p.b1 + c) : 0.f;
-    sc1v[q] = __ldg(p.stat1 + c); sh1v[q] = __ldg(p.stat1 + C + c);
-    is1v[q] = __ldg(p.stat1 + 3 * C + c); xm1v[q] = -__ldg(p.stat1 + 2 * C + c) * is1v[q];
-  }
   // ---- epilogue mapping: thread = TMEM lane (slot) 32 q + lane, columns 16 cg .. 16 cg + 15 ----
   const int eq = warp & 3, ecg = warp >> 2, eslot = eq * 32 + lane;
   // ---- sweep mapping: 8 threads per row, thread = chunks k8 and k8 + 8 of the row (channels 4 k8 .. and 32 + 4 k8 ..) ----
   const int rl = tid >> 3, k8 = tid & 7;
-  float is1s[8], xm1s[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = (i < 4) ? 4 * k8 + i : 32 + 4 * k8 + (i - 4);
-    is1s[i] = __ldg(p.stat1 + 3 * C + c);
-    xm1s[i] = -__ldg(p.stat1 + 2 * C + c) * is1s[i];
-  }
   // persistent accumulators
   float acc_a[8], acc_b[8];            // D1: sum G S0 | sum G S1;  D2T: sum dy1 | sum dy1 xhat1
   float acc_t[D2T ? 32 : 1];           // D2T: T[channel i][k]
@@ -243,9 +229,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
     mbar_wait_bounded(smem_u32(&bar_ring[st]), (uint32_t)((t / RING) & 1));
     const int4* rec_i = reinterpret_cast<const int4*>(ring + st * REC_BYTES);
     const float4* rec_a = reinterpret_cast<const float4*>(ring + st * REC_BYTES + TILE * 16);
+    // row bookkeeping of the sweep, requested now: the loads complete under the gather / MMA / epilogue phases
+    const int r_last = slot_row<MODE>(rec_i[nvalid - 1]);
+    const int pre_r = row_lo + rl;
+    int pre_b = 0, pre_e = 0;
+    if (pre_r < p.N) { pre_b = __ldg(p.rowptr + pre_r); pre_e = __ldg(p.rowptr + pre_r + 1); }
+    const int next_ptr = __ldg(p.rowptr + r_last + 1);
 
     // ================= gather: z1, a1 (bf16 hi / lo), G ==================================================
     {
+      const float4 b1q = *reinterpret_cast<const float4*>(tab + TB_B1 * C + gc * 4);
+      const float4 sc1q = *reinterpret_cast<const float4*>(tab + TB_SC1 * C + gc * 4), sh1q = *reinterpret_cast<const float4*>(tab + TB_SH1 * C + gc * 4);
+      const float4 w0q = *reinterpret_cast<const float4*>(tab + (TB_W1C + 0) * C + gc * 4), w1q = *reinterpret_cast<const float4*>(tab + (TB_W1C + 1) * C + gc * 4);
+      const float4 w2q = *reinterpret_cast<const float4*>(tab + (TB_W1C + 2) * C + gc * 4), w3q = *reinterpret_cast<const float4*>(tab + (TB_W1C + 3) * C + gc * 4);
+      const float b1v[4] = {b1q.x, b1q.y, b1q.z, b1q.w}, sc1v[4] = {sc1q.x, sc1q.y, sc1q.z, sc1q.w}, sh1v[4] = {sh1q.x, sh1q.y, sh1q.z, sh1q.w};
+      const float w1c[4][4] = {{w0q.x, w1q.x, w2q.x, w3q.x}, {w0q.y, w1q.y, w2q.y, w3q.y}, {w0q.z, w1q.z, w2q.z, w3q.z}, {w0q.w, w1q.w, w2q.w, w3q.w}};
       int4 rc[4];
       float4 pv[4], qv[4], gv[4];
       float gs[4];
@@ -311,6 +309,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
           if (gc == 0) ew_s[j] = (valid && p.ew) ? __ldg(p.ew + rc[i].z) : 1.f;
           if (valid) {
             const float atv[4] = {at.x, at.y, at.z, at.w};
+            const float4 is1q = *reinterpret_cast<const float4*>(tab + TB_IS1 * C + gc * 4), xm1q = *reinterpret_cast<const float4*>(tab + TB_XM1 * C + gc * 4);
+            const float is1v[4] = {is1q.x, is1q.y, is1q.z, is1q.w}, xm1v[4] = {xm1q.x, xm1q.y, xm1q.z, xm1q.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float xh = fmaf(z[q], is1v[q], xm1v[q]);
@@ -474,13 +474,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
 
     // ================= row sweep: segmented sums over the rows of this tile ================================
     {
-      const int r_last = slot_row<MODE>(rec_i[nvalid - 1]);
       const bool last_tile = t + 1 == ntiles;
       const int r_hi = last_tile ? r_end - 1 : r_last;
       const float* cin = carry + (t & 1) * 2 * C;
       float* cout = carry + ((t + 1) & 1) * 2 * C;
+      float is1s[8], xm1s[8];
+      if (D2) {
+        const float4 i0 = *reinterpret_cast<const float4*>(tab + TB_IS1 * C + 4 * k8), i1 = *reinterpret_cast<const float4*>(tab + TB_IS1 * C + 32 + 4 * k8);
+        const float4 m0 = *reinterpret_cast<const float4*>(tab + TB_XM1 * C + 4 * k8), m1 = *reinterpret_cast<const float4*>(tab + TB_XM1 * C + 32 + 4 * k8);
+        is1s[0] = i0.x; is1s[1] = i0.y; is1s[2] = i0.z; is1s[3] = i0.w; is1s[4] = i1.x; is1s[5] = i1.y; is1s[6] = i1.z; is1s[7] = i1.w;
+        xm1s[0] = m0.x; xm1s[1] = m0.y; xm1s[2] = m0.z; xm1s[3] = m0.w; xm1s[4] = m1.x; xm1s[5] = m1.y; xm1s[6] = m1.z; xm1s[7] = m1.w;
+      }
       for (int r = row_lo + rl; r <= r_hi; r += THREADS / 8) {
-        const int b = __ldg(p.rowptr + r), e = __ldg(p.rowptr + r + 1);
+        const int b = r == pre_r ? pre_b : __ldg(p.rowptr + r), e = r == pre_r ? pre_e : __ldg(p.rowptr + r + 1);
         const int lo = (int)(max((int64_t)b, s0) - s0), hi = (int)(min((int64_t)e, s1) - s0);
         float u[8], x[8];
 #pragma unroll
@@ -558,7 +564,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
           }
         }
       }
-      row_lo = ((int64_t)__ldg(p.rowptr + r_last + 1) > s1) ? r_last : r_last + 1;
+      row_lo = ((int64_t)next_ptr > s1) ? r_last : r_last + 1;
     }
     __syncthreads();
   }

@@ -80,6 +80,31 @@ __global__ void __launch_bounds__(1024) k_scan_widen(const int32_t* __restrict__
   }
 }
 
+
+// Per-image offsets of a collated batch (cad_recognition/train.py:238-258: a python loop over the batch items adds the
+// image's node offset to its edge rows and its proposal offset to its bbox_idx rows, in place, on the host).  Here the
+// four slice tables travel with the batch and one launch applies both offsets on the device.
+//   tab: [4][G + 1] int64 = edge slices | pos slices | bbox_idx slices | labels slices (prefix sums, tab[.][0] = 0)
+__device__ __forceinline__ int64_t slice_of(const int64_t* __restrict__ bounds, int64_t G, int64_t i) {
+  int64_t lo = 0, hi = G;            // largest g with bounds[g] <= i
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (bounds[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+__global__ void k_batch_offsets(int64_t* __restrict__ edge, int64_t E, int64_t* __restrict__ bbox_idx, int64_t N,
+                                const int64_t* __restrict__ tab, int64_t G) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t* t_edge = tab, *t_pos = tab + (G + 1), *t_bidx = tab + 2 * (G + 1), *t_lab = tab + 3 * (G + 1);
+  if (i < E) {
+    const int64_t off = t_pos[slice_of(t_edge, G, i)];
+    edge[2 * i] += off;
+    edge[2 * i + 1] += off;
+  }
+  if (i < N) bbox_idx[i] += t_lab[slice_of(t_bidx, G, i)];
+}
+
 }  // namespace yolat
 
 using namespace yolat;
@@ -119,6 +144,16 @@ int yolat_slice_graph(const int64_t* pos_idx, int64_t Np, const int64_t* edge_id
     k_edge_renumber<<<(unsigned)cdiv(Ep, 256), 256, 0, st>>>(edge, edge_idx, Ep, E_all, N_all, o2n, edge_out);
     YOLAT_CHECK_LAUNCH();
   }
+  return YOLAT_OK;
+}
+
+// edge [E, 2] and bbox_idx [N] are updated in place; tab [4][G + 1] as described at k_batch_offsets.
+int yolat_batch_offsets(int64_t* edge, int64_t E, int64_t* bbox_idx, int64_t N, const int64_t* tab, int64_t G, void* stream) {
+  if (E < 0 || N < 0 || G < 1 || !tab || (E > 0 && !edge) || (N > 0 && !bbox_idx)) return YOLAT_ERR_INVALID;
+  const int64_t n = E > N ? E : N;
+  if (n == 0) return YOLAT_OK;
+  k_batch_offsets<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(edge, E, bbox_idx, N, tab, G);
+  YOLAT_CHECK_LAUNCH();
   return YOLAT_OK;
 }
 

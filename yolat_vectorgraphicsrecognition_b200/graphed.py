@@ -55,7 +55,7 @@ class GraphedStep(object):
     @staticmethod
     def signature(batch):
         if isinstance(batch, PackedBatch):
-            return batch.signature()
+            return batch.signature() + (bool(getattr(batch, 'offsets_pending', False)),)
         return tuple((f, tuple(getattr(batch, f).shape), getattr(batch, f).dtype) for f in _FIELDS)
 
     def _sync_extra(self):
@@ -63,6 +63,9 @@ class GraphedStep(object):
             self._extra_owner.sync_hyperparams()
 
     def _eager(self, static, run_extra=True):
+        if getattr(static, '_apply_offsets', False):     # batch.collate(...).defer_offsets(): train.py:238-258 on the device
+            from .batch import apply_offsets
+            apply_offsets(static)
         out = self.model(static, None)
         loss = self.criterion(out, static)['loss']
         loss.backward()
@@ -83,6 +86,7 @@ class GraphedStep(object):
     def _capture(self, batch):
         if isinstance(batch, PackedBatch):
             buf, static = batch.device_twin(self.device)
+            static._apply_offsets = bool(getattr(batch, 'offsets_pending', False))
         else:
             buf = None
             static = SimpleNamespace(**{f: torch.empty_like(getattr(batch, f), device=self.device) for f in _FIELDS})
