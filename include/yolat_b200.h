@@ -247,6 +247,25 @@ int yolat_slice_graph(const int64_t* pos_idx, int64_t Np, const int64_t* edge_id
                       int64_t* bbox_idx_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * One-layer edge convolutions of the same family -- GraphConv(conv = 'edge' | 'attr_edge' | 'attr_edge_gp')
+ * (gcn_lib/sparse/torch_vertex.py:738-747; EdgConv :546-557 / WeightedRelativeEdgeConv :427-484, AttrEdgConv :560-573 /
+ * AttrRelativeEdgeConv :219-286, EdgConvGlobalPool :575-590 / AttrRelativeEdgeConvGlobalPool :343-425):
+ *     out[i] (pre-filled by the caller with lin_r(x) etc.) += mean_{e -> i} w_e relu(bn(W1 [x_i | x_j - x_i | attr_e] + b1))
+ * w1 [C, 2Cin+4] is the recipe's Linear weight embedded in that column layout (zero blocks for parts the recipe's
+ * concat does not have); 'multilayer_edge' (:593-605, two stages) maps onto yolat_gp2_* the same way.  C in {32,64,128}.
+ * Tape: z1 [E, C] + the BN statistic block (yolat_edge1_tape_floats); ws: yolat_edge1_ws_floats.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t yolat_edge1_tape_floats(int64_t N, int64_t E, int Cin, int C);
+int64_t yolat_edge1_ws_floats(int64_t N, int64_t E, int Cin, int C);
+int yolat_edge1_fwd(const float* w1, const float* b1, const yolat_bn* bn, int Cin, int C, const float* x, int64_t ldx,
+                    const float* attr, const float* edge_weight, const int32_t* graph, int64_t N, int64_t E, int training,
+                    float* out, int64_t ldo, float* tape, int64_t tape_floats, float* ws, int64_t ws_floats, void* stream);
+int yolat_edge1_bwd(const float* w1, const yolat_bn* bn, int Cin, int C, const float* x, int64_t ldx, const float* attr,
+                    const float* edge_weight, const int32_t* graph, int64_t N, int64_t E, int training, const float* g_out,
+                    int64_t ldgo, float* dx, int64_t lddx, int accumulate_dx, float* dw1, float* db1, float* dgamma,
+                    float* dbeta, const float* tape, float* ws, int64_t ws_floats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Per-image index offsets of a collated batch (cad_recognition/train.py:238-258: python loop over the batch items on
  * host tensors).  edge [E,2] += node offset of the edge's image, bbox_idx [N] += proposal offset of the node's image,
  * in place, one launch.  tab: [4][G+1] int64 prefix sums (device): edge slices | pos slices | bbox_idx slices |

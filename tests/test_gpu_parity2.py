@@ -119,11 +119,12 @@ def test_model_matches_oracle_full_config(config):
             # End-to-end gradients are not reproducible to 1e-4 by ANY fp32 implementation at this size (SURVEY.md
             # fact 10, section 8c: 2-5e-3 expected at config 2): the per-proposal arg-max of 1.28 M (proposal, channel)
             # pairs and ~25 M ReLU masks flip wherever two candidates are closer than the forward's rounding error,
-            # and every flip re-routes one gradient element.  Bounds: the classifier head (downstream of every flip
-            # but its own) 1e-3; everything upstream of the pooling max(2 x the fp32 restatement's own error, 1e-2).
+            # and every flip re-routes one gradient element (tools/e2e_noise.py: the fp32 restatement itself is 1-2e-3
+            # off its fp64 run on most tensors; this engine's worst tensor 2.6e-3, median 1.7e-3 with the
+            # round-to-nearest 3xTF32 split).  Bound: max(5e-3, 2 x the fp32 restatement's own error on the tensor).
             rel = float((p.grad.double().cpu() - g).norm() / g.norm())
             noise = float((ref32['grads'][k].double() - g).norm() / g.norm())
-            bound = max(1e-3, 2.0 * noise) if k.startswith('prediction_cls') else max(1e-2, 2.0 * noise)
+            bound = max(5e-3, 2.0 * noise)
             worst[k] = (rel, noise)
             assert rel < bound, (k, rel, noise)
     for k, v in st.items():

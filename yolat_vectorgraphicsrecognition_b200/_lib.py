@@ -55,6 +55,12 @@ _SIGS = {
                                 vp, i64, vp, i64, vp, i64, vp, i64, vp]),
     'yolat_gp2_bwd': (C.c_int, [C.POINTER(Gp2Params), C.POINTER(Gp2Grads), i32, i32, i32, vp, i64, vp, i64, vp, vp, vp,
                                 i64, i64, i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, vp, vp, i64, vp]),
+    'yolat_edge1_tape_floats': (i64, [i64, i64, i32, i32]),
+    'yolat_edge1_ws_floats': (i64, [i64, i64, i32, i32]),
+    'yolat_edge1_fwd': (C.c_int, [vp, vp, C.POINTER(YolatBn), i32, i32, vp, i64, vp, vp, vp, i64, i64, i32, vp, i64, vp, i64,
+                                  vp, i64, vp]),
+    'yolat_edge1_bwd': (C.c_int, [vp, C.POINTER(YolatBn), i32, i32, vp, i64, vp, vp, vp, i64, i64, i32, vp, i64, vp, i64, i32,
+                                  vp, vp, vp, vp, vp, vp, i64, vp]),
     'yolat_gemm_ws_floats': (i64, [i32, i64, i64, i64]),
     'yolat_gemm': (C.c_int, [i32, vp, i64, vp, i64, vp, i64, i64, i64, i64, vp, i32, vp, i64, vp]),
     'yolat_mlp_tape_floats': (i64, [i64, i32, i32, i32]),

@@ -374,6 +374,100 @@ static int gp2_bwd_impl(const yolat_gp2_params* p, const yolat_gp2_grads* gr, in
   return YOLAT_OK;
 }
 
+// ---- one-layer edge convolutions of the same family ----------------------------------------------------------------
+// 'edge' / 'attr_edge' / 'attr_edge_gp' of gcn_lib/sparse/torch_vertex.py (:427-484 + :546-557, :219-286 + :560-573,
+// :343-425 + :575-590): message = nn(cat(...)) with nn = MLP([F, C], 'relu', 'batch') -- ONE [Linear, BN, ReLU] stage --
+// optionally scaled by the edge weight, mean aggregation at the target.  The host embeds the recipe's Linear weight into
+// the GP2 column layout [x_i | x_j - x_i | attr] (zero blocks for absent parts), so the node-level P | Q trick applies:
+//   z1 = P[i] + Q[j] + W1c attr + b1 ;  out[i] = base[i] + mean_{e -> i} w_e relu(bn(z1_e)).
+// Tape: z1 [E, C] in slot order + the BN statistic block (these recipes are not on the timed path).
+struct Edge1Tape { float* z1; float* stat1; };
+static void edge1_tape_layout(Arena& t, int64_t E, int C, Edge1Tape* o) {
+  o->z1 = t.take(E * C);
+  o->stat1 = t.take(4 * C);
+}
+
+static int edge1_fwd_impl(const float* w1, const float* b1, const yolat_bn* bn, int Cin, int C, const float* x, int64_t ldx,
+                          const float* attr, const float* ew, const int32_t* graph, int64_t N, int64_t E, int training,
+                          float* out, int64_t ldo, Arena& tape, Arena& ws, cudaStream_t st) {
+  const bool dry = ws.dry();
+  Edge1Tape t;
+  edge1_tape_layout(tape, E, C, &t);
+  float* wpq = ws.take((int64_t)2 * C * Cin);
+  float* pq = ws.take(N * 2 * C);
+  const int nparts = edge_z1_nparts(N);
+  float* part1 = ws.take((int64_t)nparts * 2 * C);
+  if (!dry && (ws.overflow || tape.overflow)) return YOLAT_ERR_WORKSPACE;
+  if (E <= 0) return YOLAT_OK;                 // out keeps `base` (the caller pre-filled it)
+  GraphView g;
+  if (!dry) {
+    graph_layout(N, E, graph, &g);
+    YOLAT_TRY(edge_prep_wpq(w1, Cin, C, wpq, nullptr, nullptr, nullptr, st));
+  }
+  {
+    GemmArgs a{};
+    a.A = x; a.lda = ldx; a.B = wpq; a.ldb = Cin; a.C = pq; a.ldc = 2 * C; a.M = (int)N; a.N = 2 * C; a.K = Cin;
+    YOLAT_TRY(gemm(a, GEMM_NT, ws, st));
+  }
+  if (!dry) {
+    YOLAT_TRY(edge_z1(g, N, C, pq, attr, w1, Cin, b1, t.z1, training ? part1 : nullptr, st));
+    YOLAT_TRY(bn_finalize_from_partials(part1, nparts, E, C, bn, training, t.stat1, st));
+    YOLAT_TRY(edge_agg(g, N, C, t.z1, t.stat1, ew, out, ldo, out, ldo, st));
+  }
+  return YOLAT_OK;
+}
+
+static int edge1_bwd_impl(const float* w1, const yolat_bn* bn, int Cin, int C, const float* x, int64_t ldx, const float* attr,
+                          const float* ew, const int32_t* graph, int64_t N, int64_t E, int training, const float* g_out,
+                          int64_t ldgo, float* dx, int64_t lddx, int accumulate_dx, float* dw1, float* db1, float* dgamma,
+                          float* dbeta, Arena& tape, Arena& ws, cudaStream_t st) {
+  const bool dry = ws.dry();
+  Edge1Tape t;
+  edge1_tape_layout(tape, E, C, &t);
+  const int ld1 = 2 * Cin + 4;
+  if (E <= 0) {
+    if (!dry) {
+      YOLAT_TRY(zero_opt(dw1, (int64_t)C * ld1, st)); YOLAT_TRY(zero_opt(db1, C, st));
+      YOLAT_TRY(zero_opt(dgamma, C, st)); YOLAT_TRY(zero_opt(dbeta, C, st));
+      if (dx && !accumulate_dx) YOLAT_TRY(fill_zero(dx, N * lddx, st));   // lddx == Cin: contiguous
+    }
+    return YOLAT_OK;
+  }
+  GraphView g;
+  if (!dry) graph_layout(N, E, graph, &g);
+  float* dz1 = ws.take(E * C);
+  float* dpq = ws.take(N * 2 * C);
+  float* wpq = ws.take((int64_t)2 * C * Cin);
+  float* dwpq = ws.take((int64_t)2 * C * Cin);
+  float* dw1c = ws.take((int64_t)C * 4);
+  const int nparts = edge_z1_nparts(N);
+  float* partw = ws.take((int64_t)nparts * C * 4);
+  {   // BN + ReLU backward with the mean-aggregation gather fused in
+    BnBwdArgs b{};
+    b.gy = g_out; b.ldgy = ldgo; b.row_idx = dry ? nullptr : g.dst_t; b.row_scale = dry ? nullptr : g.deg_inv;
+    if (ew) { b.slot_idx = g.eid_t; b.slot_scale = ew; }
+    b.z = t.z1; b.ldz = C; b.M = E; b.C = C; b.stat = t.stat1; b.gamma = dry ? nullptr : bn->w;
+    b.relu = 1; b.training = training; b.dz = dz1; b.lddz = C; b.dgamma = dgamma; b.dbeta = dbeta; b.dbias = db1;
+    YOLAT_TRY(bn_backward(b, ws, st));
+  }
+  if (!dry) YOLAT_TRY(edge_bwd_scatter(g, N, C, dz1, attr, dpq, partw, dw1c, st));
+  if (dw1 || dry) {
+    GemmArgs a{};
+    a.A = dpq; a.lda = 2 * C; a.B = x; a.ldb = ldx; a.C = dwpq; a.ldc = Cin; a.M = 2 * C; a.N = Cin; a.K = N;
+    YOLAT_TRY(gemm(a, GEMM_TN, ws, st));
+    if (!dry && dw1) YOLAT_TRY(edge_assemble_dw1(dwpq, dw1c, Cin, C, dw1, st));
+  }
+  if (dx || dry) {
+    if (!dry) YOLAT_TRY(edge_prep_wpq(w1, Cin, C, wpq, nullptr, nullptr, nullptr, st));
+    GemmArgs a{};
+    a.A = dpq; a.lda = 2 * C; a.B = wpq; a.ldb = Cin; a.C = dx; a.ldc = lddx; a.M = (int)N; a.N = Cin; a.K = 2 * C;
+    a.accumulate = accumulate_dx;
+    YOLAT_TRY(gemm(a, GEMM_NN, ws, st));
+  }
+  if (!dry && ws.overflow) return YOLAT_ERR_WORKSPACE;
+  return YOLAT_OK;
+}
+
 }  // namespace yolat
 
 using namespace yolat;
@@ -442,6 +536,46 @@ int yolat_gp2_bwd(const yolat_gp2_params* p, const yolat_gp2_grads* g, int Cin, 
   Arena t(const_cast<float*>(tape), yolat_gp2_tape_floats_mode(N, E, Cin, Cn, C, training)), w(ws, ws_floats);
   return gp2_bwd_impl(p, g, Cin, Cn, C, x, ldx, x_node, ldxn, attr, edge_weight, graph, N, E, training, g_out, ldgo,
                       g_xnode, ldgx, dx, lddx, dx_node, lddxn, accumulate_dx, t, w, (cudaStream_t)stream);
+}
+
+int64_t yolat_edge1_tape_floats(int64_t N, int64_t E, int Cin, int C) {
+  (void)N; (void)Cin;
+  Arena t(nullptr, 0);
+  Edge1Tape o;
+  edge1_tape_layout(t, E, C, &o);
+  return t.off;
+}
+
+int64_t yolat_edge1_ws_floats(int64_t N, int64_t E, int Cin, int C) {
+  if (!gp2_channels_ok(Cin, Cin, C)) return -1;
+  Arena t1(nullptr, 0), w1(nullptr, 0), t2(nullptr, 0), w2(nullptr, 0);
+  edge1_fwd_impl(nullptr, nullptr, nullptr, Cin, C, nullptr, Cin, nullptr, nullptr, nullptr, N, E > 0 ? E : 1, 1, nullptr, C, t1, w1, nullptr);
+  edge1_bwd_impl(nullptr, nullptr, Cin, C, nullptr, Cin, nullptr, nullptr, nullptr, N, E > 0 ? E : 1, 1, nullptr, C, nullptr, Cin, 0,
+                 nullptr, nullptr, nullptr, nullptr, t2, w2, nullptr);
+  return w1.off > w2.off ? w1.off : w2.off;
+}
+
+int yolat_edge1_fwd(const float* w1, const float* b1, const yolat_bn* bn, int Cin, int C, const float* x, int64_t ldx,
+                    const float* attr, const float* edge_weight, const int32_t* graph, int64_t N, int64_t E, int training,
+                    float* out, int64_t ldo, float* tape, int64_t tape_floats, float* ws, int64_t ws_floats, void* stream) {
+  if (!w1 || !bn || !x || !graph || !out || !tape || !ws || N <= 0 || E < 0) return YOLAT_ERR_INVALID;
+  if (E > 0 && (!attr || !aligned16(attr))) return YOLAT_ERR_INVALID;
+  if (!gp2_channels_ok(Cin, Cin, C)) return YOLAT_ERR_UNSUPPORTED;
+  if (tape_floats < yolat_edge1_tape_floats(N, E, Cin, C)) return YOLAT_ERR_WORKSPACE;
+  Arena t(tape, tape_floats), w(ws, ws_floats);
+  return edge1_fwd_impl(w1, b1, bn, Cin, C, x, ldx, attr, edge_weight, graph, N, E, training, out, ldo, t, w, (cudaStream_t)stream);
+}
+
+int yolat_edge1_bwd(const float* w1, const yolat_bn* bn, int Cin, int C, const float* x, int64_t ldx, const float* attr,
+                    const float* edge_weight, const int32_t* graph, int64_t N, int64_t E, int training, const float* g_out,
+                    int64_t ldgo, float* dx, int64_t lddx, int accumulate_dx, float* dw1, float* db1, float* dgamma,
+                    float* dbeta, const float* tape, float* ws, int64_t ws_floats, void* stream) {
+  if (!w1 || !bn || !x || !graph || !tape || !ws || !g_out || N <= 0 || E < 0) return YOLAT_ERR_INVALID;
+  if (E > 0 && (!attr || !aligned16(attr))) return YOLAT_ERR_INVALID;
+  if (!gp2_channels_ok(Cin, Cin, C)) return YOLAT_ERR_UNSUPPORTED;
+  Arena t(const_cast<float*>(tape), yolat_edge1_tape_floats(N, E, Cin, C)), w(ws, ws_floats);
+  return edge1_bwd_impl(w1, bn, Cin, C, x, ldx, attr, edge_weight, graph, N, E, training, g_out, ldgo, dx, lddx, accumulate_dx,
+                        dw1, db1, dgamma, dbeta, t, w, (cudaStream_t)stream);
 }
 
 }  // extern "C"

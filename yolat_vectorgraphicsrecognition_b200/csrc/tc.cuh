@@ -227,16 +227,18 @@ __device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
   hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
   lo = x - hi;
 }
-// Finite inputs, 1.5 instructions per value: hi = x with the low 13 mantissa bits cleared (what the tensor core reads of
-// a tf32 operand anyway), lo = x - hi exactly (same sign, 13 significant bits) through the packed FADD2.  The terms
-// 3xTF32 drops are then <= 2^-20 |a b| per product instead of 2^-22 with a rounded hi -- still at the level of the
-// fp32 accumulator's own rounding (tests/test_gpu_gemm.py: <= 1e-5 of max|ref|).
+// Finite inputs, 2.5 instructions per value: hi = x rounded to nearest at 10 mantissa bits (add half an ulp of the kept
+// field to the bit pattern, clear the low 13 bits: ties away from zero on the magnitude), lo = x - hi exactly (either
+// sign, <= 2^-12 |x|) through the packed FADD2.  The tensor core reads lo truncated to tf32: what 3xTF32 then drops is
+// <= 2^-23 |a b| per product and sign-symmetric.  (Round 1 truncated hi: one instruction cheaper, but lo was one-sided and
+// its truncation a systematic 2^-21 bias -- enough to flip ~3x more ReLU masks / arg-max picks against an fp64 run than
+// an fp32 product does, tools/e2e_noise.py.)
 __device__ __forceinline__ void store_split_fast(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, const float4& v) {
   float4 h;
-  h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-  h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-  h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-  h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+  h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u);
+  h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u);
+  h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u);
+  h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u);
   float2 l0, l1;
   asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
       : "=f"(l0.x), "=f"(l0.y) : "f"(v.x), "f"(v.y), "f"(h.x), "f"(h.y));
@@ -288,14 +290,14 @@ __device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
 }
-// Truncating split of a non-negative finite value for 3xTF32: hi = the top 19 bits (exactly what the tensor core
-// reads of a tf32 operand), lo = x - hi exactly (13 significant bits).  One LOP3 + half an FADD2 per value.
+// Round-to-nearest split of a finite value for 3xTF32: hi = x rounded at 10 mantissa bits, lo = x - hi exactly (either
+// sign).  See store_split_fast.
 __device__ __forceinline__ void store_split_trunc(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float2 a, float2 b) {
   float4 h;
-  h.x = __uint_as_float(__float_as_uint(a.x) & 0xffffe000u);
-  h.y = __uint_as_float(__float_as_uint(a.y) & 0xffffe000u);
-  h.z = __uint_as_float(__float_as_uint(b.x) & 0xffffe000u);
-  h.w = __uint_as_float(__float_as_uint(b.y) & 0xffffe000u);
+  h.x = __uint_as_float((__float_as_uint(a.x) + 0x1000u) & 0xffffe000u);
+  h.y = __uint_as_float((__float_as_uint(a.y) + 0x1000u) & 0xffffe000u);
+  h.z = __uint_as_float((__float_as_uint(b.x) + 0x1000u) & 0xffffe000u);
+  h.w = __uint_as_float((__float_as_uint(b.y) + 0x1000u) & 0xffffe000u);
   const float2 l0 = fsub2(a, make_float2(h.x, h.y)), l1 = fsub2(b, make_float2(h.z, h.w));
   *reinterpret_cast<float4*>(hi_base + off) = h;
   *reinterpret_cast<float4*>(lo_base + off) = make_float4(l0.x, l0.y, l1.x, l1.y);

@@ -125,6 +125,61 @@ class GP2ConvFn(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------------
+# one-layer edge convolutions: GraphConv('edge' | 'attr_edge' | 'attr_edge_gp')   torch_vertex.py:219-286,343-484
+# --------------------------------------------------------------------------------------------------
+class Edge1ConvFn(torch.autograd.Function):
+    """(base, x, attr, edge_weight, w1e, b1, gamma, beta) -> base + mean_{e -> i} w_e relu(bn(w1e [x_i | x_j - x_i | attr] + b1)).
+    `w1e` [C, 2 Cin + 4] is the recipe's Linear weight already embedded in the GP2 column layout (the embedding is a
+    differentiable torch op of the caller, so autograd maps the gradient back to the recipe's own weight)."""
+
+    @staticmethod
+    def forward(ctx, graph, training, buffers, base, x, attr, edge_weight, w1e, b1, gamma, beta):
+        L.require_cuda(x, w1e, base)
+        lib = L.lib()
+        x, w1e, attr = L.f32c(x), L.f32c(w1e), L.f32c(attr)
+        ew = L.f32c(edge_weight) if edge_weight is not None else None
+        N, Cin = x.shape
+        C_ = w1e.shape[0]
+        E = graph.E
+        if graph.N != N or tuple(w1e.shape) != (C_, 2 * Cin + 4) or tuple(attr.shape) != (E, 4):
+            raise ValueError('edge conv: inconsistent shapes')
+        rm, rv, nbt = buffers
+        bn = _bn_struct(gamma, beta, rm, rv, nbt if training else None)
+        out = L.f32c(base).clone()
+        ws_n = lib.yolat_edge1_ws_floats(N, E, Cin, C_)
+        if ws_n < 0:
+            raise L.YolatError('edge conv: out_channels must be 32, 64 or 128 (got %d)' % C_)
+        tape = torch.empty(max(lib.yolat_edge1_tape_floats(N, E, Cin, C_), 1), dtype=torch.float32, device=x.device)
+        ws = L.workspace.get(ws_n, x.device)
+        L.check(lib.yolat_edge1_fwd(w1e.data_ptr(), L.ptr(b1), C.byref(bn), Cin, C_, x.data_ptr(), x.stride(0), L.ptr(attr),
+                                    L.ptr(ew), graph.ptr(), N, E, int(bool(training)), out.data_ptr(), out.stride(0),
+                                    tape.data_ptr(), tape.numel(), ws.data_ptr(), ws.numel(), L.stream()), 'edge1_fwd')
+        ctx.graph, ctx.training, ctx.buffers, ctx.has_bias = graph, int(bool(training)), buffers, b1 is not None
+        ctx.dims = (N, E, Cin, C_)
+        ctx.save_for_backward(x, attr, ew, w1e, gamma, beta, tape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = L.lib()
+        x, attr, ew, w1e, gamma, beta, tape = ctx.saved_tensors
+        N, E, Cin, C_ = ctx.dims
+        g_out = L.f32c(g_out)
+        rm, rv, _ = ctx.buffers
+        bn = _bn_struct(gamma, beta, rm, rv, None)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[4] else None
+        dw = torch.empty_like(w1e)
+        db = torch.empty(C_, dtype=torch.float32, device=x.device)
+        dg, dbe = torch.empty_like(gamma), torch.empty_like(beta)
+        ws = L.workspace.get(lib.yolat_edge1_ws_floats(N, E, Cin, C_), x.device)
+        L.check(lib.yolat_edge1_bwd(w1e.data_ptr(), C.byref(bn), Cin, C_, x.data_ptr(), x.stride(0), L.ptr(attr), L.ptr(ew),
+                                    ctx.graph.ptr(), N, E, ctx.training, g_out.data_ptr(), g_out.stride(0), L.ptr(dx), Cin, 0,
+                                    dw.data_ptr(), db.data_ptr(), dg.data_ptr(), dbe.data_ptr(), tape.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), L.stream()), 'edge1_bwd')
+        return None, None, None, g_out, dx, None, None, dw, (db if ctx.has_bias else None), dg, dbe
+
+
+# --------------------------------------------------------------------------------------------------
 # one [Linear, BatchNorm1d?, ReLU?] stage of gcn_lib.sparse.MLP   gcn_lib/sparse/torch_nn.py:50-71
 # --------------------------------------------------------------------------------------------------
 class MLPStageFn(torch.autograd.Function):
