@@ -1,0 +1,76 @@
+"""2-rank NCCL check of the data-parallel gradient exchange (needs 2 GPUs, skipped otherwise):
+`dp.OverlappedGradSync` -- gradients written into one flat buffer by the backward kernels, the classifier-head bucket
+all-reduced under the rest of the backward, the remainder after it -- must leave in every p.grad the MEAN of the two
+ranks' single-rank gradients, eagerly and when both collectives are captured in the step's CUDA graph."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    from yolat_vectorgraphicsrecognition_b200 import synth, dp
+    from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
+    from yolat_vectorgraphicsrecognition_b200.graphed import GraphedStep
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        opt = synth.make_opt(n_classes=17)
+        torch.manual_seed(0)
+        model = arch.SparseCADGCN(opt).to(dev).train()
+        crit = arch.DetectionLoss(opt)
+        shards = [synth.floorplans_batch(graphs=1, n=640, e=2560, seed=1000 + r).to(dev) for r in range(world)]
+        # reference: both shards on this rank without any exchange (fresh BN buffers each time: deepcopy of the model)
+        import copy
+        per = []
+        for r in range(world):
+            m = copy.deepcopy(model)
+            crit(m(shards[r], None), shards[r])['loss'].backward()
+            per.append(torch.cat([p.grad.reshape(-1) for p in m.parameters()]))
+        want = sum(per) / world
+        sync = dp.OverlappedGradSync(model)
+        m2 = model
+        for p in m2.parameters():
+            p.grad = None
+        crit(m2(shards[rank], None), shards[rank])['loss'].backward()
+        flat = sync.finish().clone()
+        assert not sync.copy_mode
+        err_eager = float((flat - want).abs().max() / want.abs().max())
+        # the same exchange captured in the step graph (a fresh model copy would need a new arena: reuse, BN buffers differ
+        # only in running statistics, which do not enter the training-mode gradients)
+        step = GraphedStep(model, crit, extra=sync.finish)
+        step(shards[rank])
+        torch.cuda.synchronize()
+        err_graph = float((sync.flat - want).abs().max() / want.abs().max())
+        adopted = all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(sync.params, sync.views))
+        if rank == 0:
+            torch.save(dict(err_eager=err_eager, err_graph=err_graph, adopted=adopted, overlapped=sync.overlapped_bytes,
+                            total=4 * sync.numel), out)
+        sync.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
+def test_overlapped_grad_sync_nccl_world2(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'res.pt')
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert res['adopted']
+    assert res['err_eager'] < 1e-6 and res['err_graph'] < 1e-6, res
+    assert res['overlapped'] > 0.8 * res['total']

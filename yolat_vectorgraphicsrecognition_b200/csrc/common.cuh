@@ -232,7 +232,7 @@ int edge_bwd_scatter(const GraphView& g, int64_t N, int C, const float* dz1, con
                      float* part, float* dw1c, cudaStream_t st);
 
 // edge_fused.cu: the fused gather -> edge MLP (tcgen05) -> statistics / segmented mean kernel (C == 64)
-enum { EF_TAPE = 1, EF_STATS = 2, EF_AGG = 4 };
+enum { EF_TAPE = 1, EF_STATS = 2, EF_AGG = 4, EF_BSTAT = 16 };
 bool edge_fused_supported(int C);
 bool edge_fused_fits(int64_t N, int64_t ldpq);
 int edge_fused_grid(int64_t E);
@@ -251,7 +251,7 @@ int edge_fused(const GraphView& g, int64_t N, int64_t E, int flags, const float*
 // edge_bwd.cu: the tape-free backward of the fused edge path (training mode, C == 64): recompute passes D1 / D2T / D2S
 struct EdgeBwdWs {
   int grid;
-  float *rec_t, *rec_s, *Ut, *Xt, *Us, *Xs, *part1, *part_tx, *part2, *part_T, *part_w2, *bstat2, *bstat1;
+  float *rec_t, *rec_s, *rec5, *Ut, *Xt, *Us, *Xs, *part1, *part_tx, *part2, *part_T, *part_w2, *bstat2, *bstat1;
 };
 int edge_bwd_grid(int64_t E);
 void edge_bwd_layout(Arena& ws, int64_t N, int64_t E, EdgeBwdWs* o);
@@ -260,6 +260,14 @@ int edge_bwd_fused(const GraphView& g, int64_t N, int64_t E, const float* pq, in
                    const float* b2, const float* stat2, const float* gamma2, const float* ew, const float* g_out,
                    int64_t ldgo, const EdgeBwdWs& w, float* dpq, float* dw1c, float* dw2, float* db1, float* dg1,
                    float* dbe1, float* db2, float* dg2, float* dbe2, cudaStream_t st);
+
+// edge_fused2.cu: K-EDGE v6 (channel-major accumulator); same arguments as edge_fused, `rows` = base (EF_AGG, must alias
+// out) or g_out (EF_BSTAT: BN2 backward statistics -> part [grid][2][C])
+bool edge_fused2_enabled();
+int edge_fused2(const GraphView& g, int64_t N, int64_t E, int flags, const float* pq, int64_t ldpq, const float* rec,
+                const float* w1, int Cin, const float* b1, const float* stat1, const float* w2, const float* b2,
+                const float* stat2, const float* ew, float* z1, float* z2, float* part, const float* rows, int64_t ldr,
+                float* out, int64_t ldo, cudaStream_t st);
 
 int colsum(const float* a, int64_t lda, int64_t M, int C, float* out, Arena& ws, cudaStream_t st);
 int fill_zero(float* p, int64_t n, cudaStream_t st);

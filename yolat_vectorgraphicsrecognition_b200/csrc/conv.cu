@@ -103,6 +103,17 @@ static bool gp2_lite(int64_t N, int64_t E, int C, int training) {
          edge_bwd_recompute_enabled();
 }
 
+// K-EDGE v6 (edge_fused2.cu, channel-major accumulator) for the MMA passes; v5 (edge_fused.cu) with YOLAT_EF=v5 or when
+// the aggregation cannot run in place on `out`
+static int edge_fused_any(const GraphView& g, int64_t N, int64_t E, int flags, const float* pq, int64_t ldpq, const float* rec,
+                          const float* w1, int Cin, const float* b1, const float* stat1, const float* w2, const float* b2,
+                          const float* stat2, const float* ew, float* z1, float* z2, float* part, const float* base,
+                          int64_t ldb, float* out, int64_t ldo, cudaStream_t st) {
+  if (edge_fused2_enabled() && (!(flags & EF_AGG) || base == out))
+    return edge_fused2(g, N, E, flags, pq, ldpq, rec, w1, Cin, b1, stat1, w2, b2, stat2, ew, z1, z2, part, base, ldb, out, ldo, st);
+  return edge_fused(g, N, E, flags, pq, ldpq, rec, w1, Cin, b1, stat1, w2, b2, stat2, ew, z1, z2, part, base, ldb, out, ldo, st);
+}
+
 static bool gp2_channels_ok(int Cin, int Cn, int C) {
   return (C == 32 || C == 64 || C == 128) && Cin >= 1 && Cn >= 1;
 }
@@ -178,12 +189,12 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
         if (training) YOLAT_TRY(edge_stats1(g, N, E, pq, ldpq, rec, p->w1, Cin, p->b1, part1f, st));
         YOLAT_TRY(bn_finalize_from_partials(part1f, ngrid1, E, C, &p->bn1, training, t.stat1, st));
         if (training) {
-          YOLAT_TRY(edge_fused(g, N, E, EF_STATS | (no_tape ? 0 : EF_TAPE), pq, ldpq, rec, p->w1, Cin, p->b1, t.stat1,
+          YOLAT_TRY(edge_fused_any(g, N, E, EF_STATS | (no_tape ? 0 : EF_TAPE), pq, ldpq, rec, p->w1, Cin, p->b1, t.stat1,
                                p->w2, p->b2, nullptr, ew, t.z1, t.z2, part2, nullptr, 0, nullptr, 0, st));
           YOLAT_TRY(bn_finalize_from_partials(part2, ngrid, E, C, &p->bn2, 1, t.stat2, st));
           if (br) join_branch(br, 1, st);      // lin_r(x) must be in `out` before the aggregation adds to it
           if (no_tape) {
-            YOLAT_TRY(edge_fused(g, N, E, EF_AGG, pq, ldpq, rec, p->w1, Cin, p->b1, t.stat1, p->w2, p->b2, t.stat2, ew,
+            YOLAT_TRY(edge_fused_any(g, N, E, EF_AGG, pq, ldpq, rec, p->w1, Cin, p->b1, t.stat1, p->w2, p->b2, t.stat2, ew,
                                  nullptr, nullptr, nullptr, base, ldbase, out, ldo, st));
           } else {
             YOLAT_TRY(edge_agg(g, N, C, t.z2, t.stat2, ew, base, ldbase, out, ldo, st));
@@ -191,7 +202,7 @@ static int gp2_fwd_impl(const yolat_gp2_params* p, int Cin, int Cn, int C, const
         } else {
           YOLAT_TRY(bn_finalize_from_partials(nullptr, 0, E, C, &p->bn2, 0, t.stat2, st));
           if (br) join_branch(br, 1, st);
-          YOLAT_TRY(edge_fused(g, N, E, EF_AGG | (no_tape ? 0 : EF_TAPE), pq, ldpq, rec, p->w1, Cin, p->b1, t.stat1,
+          YOLAT_TRY(edge_fused_any(g, N, E, EF_AGG | (no_tape ? 0 : EF_TAPE), pq, ldpq, rec, p->w1, Cin, p->b1, t.stat1,
                                p->w2, p->b2, t.stat2, ew, t.z1, t.z2, nullptr, base, ldbase, out, ldo, st));
         }
       }

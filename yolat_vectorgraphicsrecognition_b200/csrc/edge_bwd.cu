@@ -81,7 +81,7 @@ struct Params {
   const float* g; int64_t ldg;
   float* U; float* X;         // [N, C] (D2)
   float* part;                // [grid][2][C]
-  float* part_t;              // D1: [grid][C * 4 + 4]  (sum xhat1 (x) attr | sum attr);  D2T: [grid][C * 4]
+  float* part_t;              // D2S: [grid][C * 4 + 4]  (sum xhat1 (x) attr | sum attr);  D2T: [grid][C * 4]
   float* part_w2;             // D2T: [grid][128][64]
 };
 
@@ -108,7 +108,7 @@ __device__ __forceinline__ int row_at_or_after(const Params& p, int64_t s) {
 
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
-  constexpr bool D1 = MODE == M_D1, D2 = MODE != M_D1, D2T = MODE == M_D2T;
+  constexpr bool D1 = MODE == M_D1, D2 = MODE != M_D1, D2T = MODE == M_D2T, TXA = MODE == M_D2S;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_ring[RING];
   __shared__ uint64_t bar_mma;
@@ -205,15 +205,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
   // persistent accumulators
   float acc_a[8], acc_b[8];            // D1: sum G S0 | sum G S1;  D2T: sum dy1 | sum dy1 xhat1
   float acc_t[D2T ? 32 : 1];           // D2T: T[channel i][k]
-  float acc_tx[D1 ? 16 : 1], acc_sa[D1 ? 4 : 1];   // D1 (gather mapping): sum xhat1 (x) attr, sum attr
+  float acc_tx[TXA ? 16 : 1], acc_sa[TXA ? 4 : 1];   // D2S (gather mapping): sum xhat1 (x) attr, sum attr
 #pragma unroll
   for (int i = 0; i < 8; ++i) { acc_a[i] = 0.f; acc_b[i] = 0.f; }
 #pragma unroll
   for (int i = 0; i < (D2T ? 32 : 1); ++i) acc_t[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < (D1 ? 16 : 1); ++i) acc_tx[i] = 0.f;
+  for (int i = 0; i < (TXA ? 16 : 1); ++i) acc_tx[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < (D1 ? 4 : 1); ++i) acc_sa[i] = 0.f;
+  for (int i = 0; i < (TXA ? 4 : 1); ++i) acc_sa[i] = 0.f;
 
   uint32_t mma_phase = 0;
   int row_lo = r_begin;
@@ -305,21 +305,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
           const float s = valid ? gs[i] : 0.f;
           *reinterpret_cast<float4*>(s_t + off_f(j, gc)) = make_float4(gv[i].x * s, gv[i].y * s, gv[i].z * s, gv[i].w * s);
         }
-        if (D1) {
-          if (gc == 0) ew_s[j] = (valid && p.ew) ? __ldg(p.ew + rc[i].z) : 1.f;
-          if (valid) {
-            const float atv[4] = {at.x, at.y, at.z, at.w};
-            const float4 is1q = *reinterpret_cast<const float4*>(tab + TB_IS1 * C + gc * 4), xm1q = *reinterpret_cast<const float4*>(tab + TB_XM1 * C + gc * 4);
-            const float is1v[4] = {is1q.x, is1q.y, is1q.z, is1q.w}, xm1v[4] = {xm1q.x, xm1q.y, xm1q.z, xm1q.w};
+        if (D1 && gc == 0) ew_s[j] = (valid && p.ew) ? __ldg(p.ew + rc[i].z) : 1.f;
+        if (TXA && valid) {
+          const float atv[4] = {at.x, at.y, at.z, at.w};
+          const float4 is1q = *reinterpret_cast<const float4*>(tab + TB_IS1 * C + gc * 4), xm1q = *reinterpret_cast<const float4*>(tab + TB_XM1 * C + gc * 4);
+          const float is1v[4] = {is1q.x, is1q.y, is1q.z, is1q.w}, xm1v[4] = {xm1q.x, xm1q.y, xm1q.z, xm1q.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float xh = fmaf(z[q], is1v[q], xm1v[q]);
+          for (int q = 0; q < 4; ++q) {
+            const float xh = fmaf(z[q], is1v[q], xm1v[q]);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) acc_tx[D1 ? q * 4 + k : 0] = fmaf(xh, atv[k], acc_tx[D1 ? q * 4 + k : 0]);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc_sa[D1 ? k : 0] += atv[k];
+            for (int k = 0; k < 4; ++k) acc_tx[TXA ? q * 4 + k : 0] = fmaf(xh, atv[k], acc_tx[TXA ? q * 4 + k : 0]);
           }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc_sa[TXA ? k : 0] += atv[k];
         }
       }
     }
@@ -599,14 +597,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) mine[16 + i] = acc_t[D2T ? i : 0];
     }
-    float* red2 = red + 64 * 8 * 16;                            // D1: [32 sl][16 gc][20]
-    if (D1) {
-      float* m2 = red2 + (size_t)(sl * 16 + gc) * 20;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) m2[i] = acc_tx[D1 ? i : 0];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) m2[16 + k] = acc_sa[D1 ? k : 0];
-    }
     __syncthreads();
     if (tid < 8 * NV) {
       const int kk = tid / NV, vv = tid % NV;
@@ -617,7 +607,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
       if (vv < 16) p.part[((int64_t)blockIdx.x * 2 + (vv >> 3)) * C + c] = s;
       else p.part_t[(int64_t)blockIdx.x * (C * 4) + c * 4 + ((vv - 16) & 3)] = s;
     }
-    if (D1 && tid < 16 * 20) {
+  } else {
+    float* red2 = reinterpret_cast<float*>(sm);                 // [32 sl][16 gc][20]
+    float* m2 = red2 + (size_t)(sl * 16 + gc) * 20;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m2[i] = acc_tx[TXA ? i : 0];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m2[16 + k] = acc_sa[TXA ? k : 0];
+    __syncthreads();
+    if (tid < 16 * 20) {
       const int g2 = tid / 20, vv = tid % 20;
       float s = 0.f;
       for (int q = 0; q < 32; ++q) s += red2[(size_t)(q * 16 + g2) * 20 + vv];
@@ -724,6 +722,7 @@ void edge_bwd_layout(Arena& ws, int64_t N, int64_t E, EdgeBwdWs* o) {
   o->grid = grid;
   o->rec_t = ws.take(8 * E + 8);
   o->rec_s = ws.take(8 * E + 8);
+  o->rec5 = ws.take(edge_records_floats(E));
   o->Ut = ws.take(N * eb::C); o->Xt = ws.take(N * eb::C);
   o->Us = ws.take(N * eb::C); o->Xs = ws.take(N * eb::C);
   o->part1 = ws.take((int64_t)grid * 2 * eb::C);
@@ -760,9 +759,14 @@ int edge_bwd_fused(const GraphView& g, int64_t N, int64_t E, const float* pq, in
   p.w1c = w1 + 2 * Cin; p.ld1 = 2 * Cin + 4; p.b1 = b1; p.stat1 = stat1; p.w2 = w2; p.b2 = b2; p.stat2 = stat2;
   p.ew = ew; p.g = g_out; p.ldg = ldgo;
   cudaError_t e;
-  {   // D1: BN2 backward statistics
+  if (edge_fused2_enabled()) {
+    // D1 on the channel-major forward kernel (edge_fused2.cu, F_BSTAT): its record format is the forward's
+    YOLAT_TRY(edge_records(g, E, attr, ldpq, w.rec5, st));
+    YOLAT_TRY(edge_fused2(g, N, E, EF_BSTAT, pq, ldpq, w.rec5, w1, Cin, b1, stat1, w2, b2, stat2, ew, nullptr, nullptr, w.part1,
+                          g_out, ldgo, nullptr, 0, st));
+  } else {   // D1: BN2 backward statistics
     Params q = p;
-    q.rowptr = g.rowptr_t; q.rec_idx = ri_t; q.rec_attr = ra_t; q.part = w.part1; q.part_t = w.part_tx;
+    q.rowptr = g.rowptr_t; q.rec_idx = ri_t; q.rec_attr = ra_t; q.part = w.part1;
     ProfScope prof(YOLAT_PROF_EDGE_BWD_D1, st);
     e = launch<M_D1>(q, grid, st);
     if (e != cudaSuccess) { set_last_error(e); return YOLAT_ERR_LAUNCH; }
@@ -780,7 +784,7 @@ int edge_bwd_fused(const GraphView& g, int64_t N, int64_t E, const float* pq, in
   }
   {   // D2S: row sums by source
     Params q = p;
-    q.rowptr = g.rowptr_s; q.rec_idx = ri_s; q.rec_attr = ra_s; q.bstat2 = w.bstat2; q.U = w.Us; q.X = w.Xs;
+    q.rowptr = g.rowptr_s; q.rec_idx = ri_s; q.rec_attr = ra_s; q.bstat2 = w.bstat2; q.U = w.Us; q.X = w.Xs; q.part_t = w.part_tx;
     ProfScope prof(YOLAT_PROF_EDGE_BWD_D2S, st);
     e = launch<M_D2S>(q, grid, st);
     if (e != cudaSuccess) { set_last_error(e); return YOLAT_ERR_LAUNCH; }

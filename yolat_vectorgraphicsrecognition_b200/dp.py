@@ -82,8 +82,9 @@ class OverlappedGradSync(object):
     back to the copy-then-reduce schedule of `FlatGradients`.
     """
 
-    def __init__(self, model, group=None, early_prefixes=('prediction_cls',)):
+    def __init__(self, model, group=None, early_prefixes=('prediction_cls',), overlap=True, async_early=True):
         from . import ops
+        self.overlap, self.async_early = bool(overlap), bool(async_early)
         named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
         self.params = [p for _, p in named]
         self.group = group
@@ -107,7 +108,9 @@ class OverlappedGradSync(object):
         self.copy_mode = False
         self._count = 0
         self._work = None
-        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.early_params]
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.early_params] if self.overlap else []
+        if not self.overlap:
+            self.split = self.numel           # one bucket, reduced in finish()
         self.exposed_bytes = 4 * self.split
         self.overlapped_bytes = 4 * (self.numel - self.split)
 
@@ -134,7 +137,7 @@ class OverlappedGradSync(object):
             self._work = None
         if self.world() > 1 and self.split < self.numel:
             self._work = dist.all_reduce(self.flat.narrow(0, self.split, self.numel - self.split),
-                                         op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                                         op=dist.ReduceOp.SUM, group=self.group, async_op=self.async_early)
 
     def finish(self, _loss=None):
         """Join the early collective, reduce the rest, scale: p.grad = mean over ranks for every parameter."""

@@ -28,7 +28,7 @@ _FIELDS = ('x', 'bbox_idx', 'edge', 'bbox', 'e_attr', 'labels')
 
 class GraphedStep(object):
 
-    def __init__(self, model, criterion, warmup=3, extra=None, optimizer=None):
+    def __init__(self, model, criterion, warmup=3, extra=None, optimizer=None, capture_error_mode='global'):
         """`extra(loss)` (optional) is called inside the captured region after backward -- e.g. a fused
         optimizer step or the data-parallel gradient all-reduce -- and must be capture-safe.  It is NOT run during the
         eager warm-up steps of a capture (they would be hidden optimizer updates / extra collectives); if its owner
@@ -36,10 +36,12 @@ class GraphedStep(object):
         `sync_hyperparams()` before every capture and replay (device-resident learning rate of optim.FusedAdam).
         `optimizer=` names that owner explicitly (and makes `extra` its step when no `extra` is given).
         With a collective inside `extra`, every rank must meet a new batch shape at the same step: capture is a
-        collective event."""
+        collective event.  `capture_error_mode` is passed to torch.cuda.graph ('thread_local' when autograd hooks issue
+        NCCL work from the autograd thread during capture: dp.OverlappedGradSync)."""
         if optimizer is not None and extra is None:       # GraphedStep(model, crit, optimizer=FusedAdam(...))
             extra = lambda loss: optimizer.step()
         self.model, self.criterion, self.warmup, self.extra = model, criterion, int(warmup), extra
+        self.capture_error_mode = capture_error_mode
         self._extra_owner = optimizer if optimizer is not None else getattr(extra, '__self__', None)
         if hasattr(self._extra_owner, 'prepare'):
             self._extra_owner.prepare()
@@ -109,7 +111,7 @@ class GraphedStep(object):
         graph = torch.cuda.CUDAGraph()
         for p in self.params:
             p.grad = None
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, capture_error_mode=self.capture_error_mode):
             loss, logits = self._eager(static)
         entry.graph, entry.loss, entry.logits = graph, loss, logits
         entry.grads = [p.grad for p in self.params]
