@@ -241,7 +241,8 @@ def main():
 
     # The step is ~130 short kernels: eager launching is host-bound, so the product path replays it as one CUDA
     # graph (graphed.py); at N > 1 the two NCCL all-reduces are captured into the same graph.
-    graphed = GraphedStep(model, crit, extra=sync.finish if sync is not None else None)
+    graphed = GraphedStep(model, crit, extra=sync.finish if sync is not None else None,
+                          capture_error_mode='thread_local' if sync is not None else 'global')
 
     def graph_step(batch):
         return graphed(batch)
@@ -291,10 +292,12 @@ def main():
     # ---- N > 1: how much of the collective is exposed (same step captured without it) ----------------
     collective = None
     if sync is not None and args.mode == 'graph':
+        sync.enabled = False               # the same step without any collective
         plain = GraphedStep(model, crit)
         for _ in range(3):
             plain(resident)
         ms_plain = timed(plain, resident, args.steps)
+        sync.enabled = True
         collective = {'op': 'ncclAllReduce(sum) of the flat fp32 gradient buffer, two buckets captured in the step graph',
                       'bytes': 4 * sync.numel, 'overlapped_bytes': sync.overlapped_bytes,
                       'exposed_bytes': sync.exposed_bytes, 'exposed_us': (ms - ms_plain) * 1e3,

@@ -52,7 +52,7 @@ def _worker(rank, world, port, out):
         err_eager = float((flat - want).abs().max() / want.abs().max())
         # the same exchange captured in the step graph (a fresh model copy would need a new arena: reuse, BN buffers differ
         # only in running statistics, which do not enter the training-mode gradients)
-        step = GraphedStep(model, crit, extra=sync.finish)
+        step = GraphedStep(model, crit, extra=sync.finish, capture_error_mode='thread_local')
         step(shards[rank])
         torch.cuda.synchronize()
         err_graph = float((sync.flat - want).abs().max() / want.abs().max())

@@ -461,12 +461,18 @@ static cudaError_t launch(const Params& p, int grid, cudaStream_t st) {
 
 }  // namespace ef2
 
-// YOLAT_EF=v5 selects the round-1 kernel (edge_fused.cu) for the MMA passes
+// Off by default: YOLAT_EF=v6 selects this kernel for the MMA passes and the backward statistics pass D1.
+// Measured at N = 320 000, E = 1 280 000 (profiles/r2_g_ef2_*.txt): F_STATS 144 us (v5: 130), F_AGG 821 us (v5: 172),
+// F_BSTAT 715 us (eb::k_edge_bwd<D1>: 383).  Shared-memory wavefronts drop from 17 M to 10-11 M as designed, but the
+// per-channel sweep is ONE warp per TMEM lane quarter executing ~2.4 k dependent instructions per tile next to four
+// gather warps on the same scheduler: ~10 cycles per instruction = 23 k cycles per tile.  The thread-per-slot epilogue
+// of v5 (many threads, short chains, one staging round trip) is the better balance on this machine; splitting the sweep
+// over more warps needs more than the 1024 threads a CTA can have next to 16 gather warps.
 bool edge_fused2_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("YOLAT_EF");
-    v = (e && e[0] == 'v' && e[1] == '5') ? 0 : 1;
+    v = (e && e[0] == 'v' && e[1] == '6') ? 1 : 0;
   }
   return v == 1;
 }

@@ -106,6 +106,7 @@ class OverlappedGradSync(object):
         self.views = [self.flat.narrow(0, o, p.numel()).view(p.shape) for o, p in zip(self.offsets, self.params)]
         ops.set_grad_arena({p.data_ptr(): (self.flat, o, p.numel()) for o, p in zip(self.offsets, self.params)})
         self.copy_mode = False
+        self.enabled = True           # False: the hooks do nothing (steps that must not communicate, e.g. an A/B timing)
         self._count = 0
         self._work = None
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.early_params] if self.overlap else []
@@ -123,6 +124,8 @@ class OverlappedGradSync(object):
         return all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, views))
 
     def _on_grad(self, _p):
+        if not self.enabled:
+            return
         self._count += 1
         if self._count < len(self.early_params) or self.copy_mode:
             return
@@ -132,7 +135,9 @@ class OverlappedGradSync(object):
                 raise RuntimeError('OverlappedGradSync: autograd did not adopt the flat-buffer views during capture')
             self.copy_mode = True
             return
-        if self._work is not None:                # a step whose finish() was never called (capture warm-up)
+        if self._work is not None:                # a step whose finish() was never called: see drain()
+            if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError('OverlappedGradSync: an uncaptured collective is pending; call drain() before the capture')
             self._work.wait()
             self._work = None
         if self.world() > 1 and self.split < self.numel:
@@ -167,6 +172,15 @@ class OverlappedGradSync(object):
         if world > 1:
             self.flat.mul_(1.0 / world)
         return self.flat
+
+    def drain(self):
+        """Join an early-bucket collective whose finish() was never called (the eager warm-up steps of a GraphedStep
+        capture run the backward hooks but not `extra`).  Must run OUTSIDE a capture: a captured stream may not depend on
+        uncaptured work of another stream (cudaErrorStreamCaptureIsolation)."""
+        self._count = 0
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
 
     def close(self):
         from . import ops

@@ -98,11 +98,18 @@ class GraphedStep(object):
         # pieces) must happen outside the capture; gradients are created here and stay the same tensors
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
+        restage = bool(getattr(static, '_apply_offsets', False))      # the device offsets update the inputs in place
         with torch.cuda.stream(side):
             for _ in range(self.warmup):
                 for p in self.params:
                     p.grad = None
+                if restage:
+                    self._stage(entry, batch)
                 self._eager(static, run_extra=False)
+            if restage:
+                self._stage(entry, batch)
+            if hasattr(self._extra_owner, 'drain'):      # e.g. dp.OverlappedGradSync: collectives issued by the warm-up hooks
+                self._extra_owner.drain()
         torch.cuda.current_stream(self.device).wait_stream(side)
         self._sync_extra()
         # NOTE: the warm-up steps are real training-mode forwards + backwards (without `extra`): they update the BN
