@@ -50,16 +50,19 @@ def _worker(rank, world, port, out):
         flat = sync.finish().clone()
         assert not sync.copy_mode
         err_eager = float((flat - want).abs().max() / want.abs().max())
-        # the same exchange captured in the step graph (a fresh model copy would need a new arena: reuse, BN buffers differ
-        # only in running statistics, which do not enter the training-mode gradients)
-        step = GraphedStep(model, crit, extra=sync.finish, capture_error_mode='thread_local')
+        overlapped, total = sync.overlapped_bytes, 4 * sync.numel
+        sync.close()
+        # the same exchange captured in the step graph: one bucket reduced at the end of the backward (NCCL work issued
+        # asynchronously from autograd hooks INSIDE a capture hung on this stack; hooks + capture need async_op=False or
+        # no hooks at all -- tools/nccl_capture_probe.py), still without a gather copy: the views are the gradients
+        sync = dp.OverlappedGradSync(model, overlap=False)
+        step = GraphedStep(model, crit, extra=sync.finish)
         step(shards[rank])
         torch.cuda.synchronize()
         err_graph = float((sync.flat - want).abs().max() / want.abs().max())
         adopted = all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(sync.params, sync.views))
         if rank == 0:
-            torch.save(dict(err_eager=err_eager, err_graph=err_graph, adopted=adopted, overlapped=sync.overlapped_bytes,
-                            total=4 * sync.numel), out)
+            torch.save(dict(err_eager=err_eager, err_graph=err_graph, adopted=adopted, overlapped=overlapped, total=total), out)
         sync.close()
     finally:
         dist.destroy_process_group()

@@ -41,24 +41,32 @@ namespace eb {
 using namespace tc;
 
 constexpr int C = 64;
-constexpr int TILE = 128;
-constexpr int THREADS = 512;
 constexpr int RING = 3;
-constexpr uint32_t T_BF = TILE * 128;               // one bf16 tile [128 slots][64 channels]: 16 KB
-constexpr uint32_t OFF_A1 = 0;                      // a1 hi | mid | lo
-constexpr uint32_t OFF_DZ = OFF_A1 + 3 * T_BF;      // dz2 hi | lo
-constexpr uint32_t OFF_W2 = OFF_DZ + 2 * T_BF;      // W2 hi | mid | lo, [64 out][64 in] bf16, 8 KB each
-constexpr uint32_t W_BF = 64 * 128;
-constexpr uint32_t OFF_ZT = OFF_W2 + 3 * W_BF;      // z1 tile, fp32 [128][64], chunk-swizzled
-constexpr uint32_t OFF_ST = OFF_ZT + TILE * 256;    // G -> dy1 (D2) | xhat2 with the mask in the lowest mantissa bit (D1)
-constexpr uint32_t OFF_REC = OFF_ST + TILE * 256;   // record ring: RING x (128 x int4 | 128 x float4)
-constexpr uint32_t REC_BYTES = TILE * 32;
-constexpr uint32_t OFF_TAB = OFF_REC + RING * REC_BYTES;   // per-channel tables, 16 x 64 floats
-constexpr uint32_t OFF_EW = OFF_TAB + 16 * 256;     // edge weight per slot (D1)
-constexpr uint32_t OFF_CARRY = OFF_EW + TILE * 4;   // [2 parities][U | X][64]
-constexpr uint32_t SMEM_BYTES = OFF_CARRY + 2 * 2 * 256 + 1024;
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_REC >= 64 * 8 * 48 * 4 && OFF_REC >= (64 * 8 * 16 + 32 * 16 * 20) * 4, "the final reduction aliases the tiles");
+constexpr uint32_t W_BF = 64 * 128;                   // one bf16 part of W2 [64 out][64 in]: 8 KB
+// Tile geometry.  TILE = 128: one CTA of 512 threads per SM.  TILE = 64: 256 threads, TWO CTAs per SM -- the phases of a
+// tile are bulk-synchronous (every phase starts with loads nothing overlaps, both MMA waits idle the whole CTA), so a
+// second resident CTA is what fills those gaps; the M = 64 accumulators of z2 / da1 then keep rows 16 q .. 16 q + 15 in
+// TMEM lanes 32 q .. 32 q + 15 (tools/umma_probe_m64.cu): half of each epilogue warp idles in the two epilogue phases.
+template <int TILE>
+struct L {
+  static constexpr int THREADS = TILE * 4;
+  static constexpr int SLG = THREADS / 16;             // slot groups of the gather: slot = sl + SLG * i, i < 4
+  static constexpr int NCOL = TILE == 128 ? 16 : 32;   // accumulator columns per epilogue thread
+  static constexpr uint32_t T_BF = TILE * 128;         // one bf16 tile [TILE slots][64 channels]
+  static constexpr uint32_t OFF_A1 = 0;                // a1 hi | mid | lo
+  static constexpr uint32_t OFF_DZ = OFF_A1 + 3 * T_BF;   // dz2 hi | lo
+  static constexpr uint32_t OFF_W2 = OFF_DZ + 2 * T_BF;   // W2 hi | mid | lo
+  static constexpr uint32_t OFF_ZT = OFF_W2 + 3 * W_BF;   // z1 tile, fp32 [TILE][64], chunk-swizzled
+  static constexpr uint32_t OFF_ST = OFF_ZT + TILE * 256; // G -> dy1 (D2) | xhat2 with the mask in the lowest mantissa bit (D1)
+  static constexpr uint32_t OFF_REC = OFF_ST + TILE * 256;   // record ring: RING x (TILE x int4 | TILE x float4)
+  static constexpr uint32_t REC_BYTES = TILE * 32;
+  static constexpr uint32_t OFF_TAB = OFF_REC + RING * REC_BYTES;   // per-channel tables, 16 x 64 floats
+  static constexpr uint32_t OFF_EW = OFF_TAB + 16 * 256;  // edge weight per slot (D1)
+  static constexpr uint32_t OFF_CARRY = OFF_EW + TILE * 4;   // [2 parities][U | X][64]
+  static constexpr uint32_t SMEM_BYTES = OFF_CARRY + 2 * 2 * 256 + 1024;
+  static_assert(SMEM_BYTES * (TILE == 64 ? 2 : 1) <= 226 * 1024, "shared memory budget");
+  static_assert(OFF_REC >= (THREADS / 8) * 8 * 48 * 4 && OFF_REC >= (SLG * 16 * 20) * 4, "the final reduction aliases the tiles");
+};
 
 enum { M_D1 = 0, M_D2T = 1, M_D2S = 2 };
 // per-channel tables
@@ -93,6 +101,9 @@ __device__ __forceinline__ uint32_t off_f(int slot, int chunk) {  // chunk: 16-b
   return (uint32_t)slot * 256u + ((((uint32_t)chunk) ^ ((uint32_t)slot & 15u)) << 4);
 }
 
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+
 template <int MODE>
 __device__ __forceinline__ int slot_row(const int4& r) { return MODE == M_D2S ? r.y : r.x; }
 
@@ -106,8 +117,11 @@ __device__ __forceinline__ int row_at_or_after(const Params& p, int64_t s) {
   return (p.rowptr[v] == (int32_t)s) ? v : v + 1;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
+template <int MODE, int TILE>
+__global__ void __launch_bounds__(L<TILE>::THREADS, TILE == 64 ? 2 : 1) k_edge_bwd(const Params p) {
+  using LT = L<TILE>;
+  constexpr int THREADS = LT::THREADS, SLG = LT::SLG, NCOL = LT::NCOL;
+  constexpr uint32_t T_BF = LT::T_BF, REC_BYTES = LT::REC_BYTES;
   constexpr bool D1 = MODE == M_D1, D2 = MODE != M_D1, D2T = MODE == M_D2T, TXA = MODE == M_D2S;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_ring[RING];
@@ -118,15 +132,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
   const uint32_t pad = ((raw_u32 + 1023u) & ~1023u) - raw_u32;
   uint8_t* sm = smem_raw + pad;
   const uint32_t sm_u32 = raw_u32 + pad;
-  uint8_t* a1_t = sm + OFF_A1;
-  uint8_t* dz_t = sm + OFF_DZ;
-  uint8_t* w2_t = sm + OFF_W2;
-  uint8_t* z_t = sm + OFF_ZT;
-  uint8_t* s_t = sm + OFF_ST;
-  uint8_t* ring = sm + OFF_REC;
-  float* tab = reinterpret_cast<float*>(sm + OFF_TAB);
-  float* ew_s = reinterpret_cast<float*>(sm + OFF_EW);
-  float* carry = reinterpret_cast<float*>(sm + OFF_CARRY);
+  uint8_t* a1_t = sm + LT::OFF_A1;
+  uint8_t* dz_t = sm + LT::OFF_DZ;
+  uint8_t* w2_t = sm + LT::OFF_W2;
+  uint8_t* z_t = sm + LT::OFF_ZT;
+  uint8_t* s_t = sm + LT::OFF_ST;
+  uint8_t* ring = sm + LT::OFF_REC;
+  float* tab = reinterpret_cast<float*>(sm + LT::OFF_TAB);
+  float* ew_s = reinterpret_cast<float*>(sm + LT::OFF_EW);
+  float* carry = reinterpret_cast<float*>(sm + LT::OFF_CARRY);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -196,10 +210,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
   };
   if (tid == 0) { fill(0); fill(1); }
 
-  // ---- gather mapping: thread (gc, sl) = channels 4 gc .. 4 gc + 3 of slots sl + 32 i (constants come from the tables) ----
+  // ---- gather mapping: thread (gc, sl) = channels 4 gc .. 4 gc + 3 of slots sl + SLG i (constants come from the tables) ----
   const int gc = tid & 15, sl = tid >> 4;
-  // ---- epilogue mapping: thread = TMEM lane (slot) 32 q + lane, columns 16 cg .. 16 cg + 15 ----
-  const int eq = warp & 3, ecg = warp >> 2, eslot = eq * 32 + lane;
+  // ---- epilogue mapping: warp quarter eq <-> TMEM lanes 32 eq .., NCOL columns from NCOL * ecg.  M = 128 accumulators: thread =
+  //      slot 32 eq + lane; M = 64: slot 16 eq + lane for lane < 16 (the other half of the warp has no row) ----
+  const int eq = warp & 3, ecg = warp >> 2;
+  const int eslot = TILE == 128 ? eq * 32 + lane : eq * 16 + (lane & 15);
+  const bool eact = TILE == 128 || lane < 16;
   // ---- sweep mapping: 8 threads per row, thread = chunks k8 and k8 + 8 of the row (channels 4 k8 .. and 32 + 4 k8 ..) ----
   const int rl = tid >> 3, k8 = tid & 7;
   // persistent accumulators
@@ -242,14 +259,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
       const float4 sc1q = *reinterpret_cast<const float4*>(tab + TB_SC1 * C + gc * 4), sh1q = *reinterpret_cast<const float4*>(tab + TB_SH1 * C + gc * 4);
       const float4 w0q = *reinterpret_cast<const float4*>(tab + (TB_W1C + 0) * C + gc * 4), w1q = *reinterpret_cast<const float4*>(tab + (TB_W1C + 1) * C + gc * 4);
       const float4 w2q = *reinterpret_cast<const float4*>(tab + (TB_W1C + 2) * C + gc * 4), w3q = *reinterpret_cast<const float4*>(tab + (TB_W1C + 3) * C + gc * 4);
-      const float b1v[4] = {b1q.x, b1q.y, b1q.z, b1q.w}, sc1v[4] = {sc1q.x, sc1q.y, sc1q.z, sc1q.w}, sh1v[4] = {sh1q.x, sh1q.y, sh1q.z, sh1q.w};
-      const float w1c[4][4] = {{w0q.x, w1q.x, w2q.x, w3q.x}, {w0q.y, w1q.y, w2q.y, w3q.y}, {w0q.z, w1q.z, w2q.z, w3q.z}, {w0q.w, w1q.w, w2q.w, w3q.w}};
+      const float2 bp[2] = {make_float2(b1q.x, b1q.y), make_float2(b1q.z, b1q.w)};
+      const float2 scp[2] = {make_float2(sc1q.x, sc1q.y), make_float2(sc1q.z, sc1q.w)};
+      const float2 shp[2] = {make_float2(sh1q.x, sh1q.y), make_float2(sh1q.z, sh1q.w)};
+      const float2 wp[4][2] = {{make_float2(w0q.x, w0q.y), make_float2(w0q.z, w0q.w)}, {make_float2(w1q.x, w1q.y), make_float2(w1q.z, w1q.w)},
+                               {make_float2(w2q.x, w2q.y), make_float2(w2q.z, w2q.w)}, {make_float2(w3q.x, w3q.y), make_float2(w3q.z, w3q.w)}};
+      // store offsets of slot sl + SLG i (SLG is a multiple of 16): the swizzle terms depend on sl only
+      const uint32_t fbase = (uint32_t)sl * 256u + ((((uint32_t)gc) ^ ((uint32_t)sl & 15u)) << 4);
+      const uint32_t bbase = (uint32_t)(sl >> 3) * 1024u + (uint32_t)(sl & 7) * 128u + (((((uint32_t)gc * 4u) >> 3) ^ ((uint32_t)sl & 7u)) << 4) +
+                             (((uint32_t)gc * 4u) & 7u) * 2u;
       int4 rc[4];
       float4 pv[4], qv[4], gv[4];
       float gs[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int j = sl + 32 * i;
+        const int j = sl + SLG * i;
         rc[i] = rec_i[j];
         pv[i] = __ldg(reinterpret_cast<const float4*>(pq_b + (uint32_t)rc[i].x * ldpq_b + (uint32_t)gc * 16u));
         qv[i] = __ldg(reinterpret_cast<const float4*>(pq_b + (uint32_t)rc[i].y * ldpq_b + (uint32_t)(C * 4 + gc * 16)));
@@ -266,7 +290,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
         const int4* rn = reinterpret_cast<const int4*>(ring + stn * REC_BYTES);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int4 r = rn[sl + 32 * i];
+          const int4 r = rn[sl + SLG * i];
           const char* a = gc < 2 ? pq_b + (uint32_t)r.x * ldpq_b + (uint32_t)gc * 128u
                         : gc < 4 ? pq_b + (uint32_t)r.y * ldpq_b + (uint32_t)(C * 4) + (uint32_t)(gc - 2) * 128u
                                  : reinterpret_cast<const char*>(p.g + (int64_t)r.x * p.ldg) + (gc - 4) * 128;
@@ -275,35 +299,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int j = sl + 32 * i;
+        const int j = sl + SLG * i;
         const bool valid = j < nvalid;
         const float4 at = rec_a[j];
-        float z[4];
-        const float pp[4] = {pv[i].x, pv[i].y, pv[i].z, pv[i].w}, qq[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w};
+        // same association as the forward passes: ((W1c attr + b1) + P) + Q, in packed fp32 pairs
+        float2 v0 = ffma2s(at.x, wp[0][0], bp[0]), v1 = ffma2s(at.x, wp[0][1], bp[1]);
+        v0 = ffma2s(at.y, wp[1][0], v0); v1 = ffma2s(at.y, wp[1][1], v1);
+        v0 = ffma2s(at.z, wp[2][0], v0); v1 = ffma2s(at.z, wp[2][1], v1);
+        v0 = ffma2s(at.w, wp[3][0], v0); v1 = ffma2s(at.w, wp[3][1], v1);
+        v0 = fadd2(fadd2(v0, make_float2(pv[i].x, pv[i].y)), make_float2(qv[i].x, qv[i].y));
+        v1 = fadd2(fadd2(v1, make_float2(pv[i].z, pv[i].w)), make_float2(qv[i].z, qv[i].w));
+        const float z[4] = {v0.x, v0.y, v1.x, v1.y};
+        float2 a0 = ffma2(v0, scp[0], shp[0]), a1 = ffma2(v1, scp[1], shp[1]);
         float4 a;
-        float av[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          // same association as the forward passes: ((W1c attr + b1) + P) + Q
-          float v = fmaf(at.x, w1c[q][0], b1v[q]);
-          v = fmaf(at.y, w1c[q][1], v);
-          v = fmaf(at.z, w1c[q][2], v);
-          v = fmaf(at.w, w1c[q][3], v);
-          v = (v + pp[q]) + qq[q];
-          z[q] = v;
-          av[q] = valid ? fmaxf(fmaf(v, sc1v[q], sh1v[q]), 0.f) : 0.f;
-        }
-        a = make_float4(av[0], av[1], av[2], av[3]);
-        *reinterpret_cast<float4*>(z_t + off_f(j, gc)) = make_float4(z[0], z[1], z[2], z[3]);
+        a.x = valid ? fmaxf(a0.x, 0.f) : 0.f; a.y = valid ? fmaxf(a0.y, 0.f) : 0.f;
+        a.z = valid ? fmaxf(a1.x, 0.f) : 0.f; a.w = valid ? fmaxf(a1.y, 0.f) : 0.f;
+        *reinterpret_cast<float4*>(z_t + fbase + (uint32_t)i * (SLG * 256u)) = make_float4(z[0], z[1], z[2], z[3]);
         uint2 hi, mid, lo;
         split3_bf16x4(a, hi, mid, lo);
-        const uint32_t ob = off_bf(j, gc * 4);
+        const uint32_t ob = bbase + (uint32_t)i * (SLG / 8 * 1024u);
         *reinterpret_cast<uint2*>(a1_t + ob) = hi;
         *reinterpret_cast<uint2*>(a1_t + T_BF + ob) = mid;
         *reinterpret_cast<uint2*>(a1_t + 2 * T_BF + ob) = lo;
         if (D2) {
           const float s = valid ? gs[i] : 0.f;
-          *reinterpret_cast<float4*>(s_t + off_f(j, gc)) = make_float4(gv[i].x * s, gv[i].y * s, gv[i].z * s, gv[i].w * s);
+          *reinterpret_cast<float4*>(s_t + fbase + (uint32_t)i * (SLG * 256u)) = make_float4(gv[i].x * s, gv[i].y * s, gv[i].z * s, gv[i].w * s);
         }
         if (D1 && gc == 0) ew_s[j] = (valid && p.ew) ? __ldg(p.ew + rc[i].z) : 1.f;
         if (TXA && valid) {
@@ -329,7 +349,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
       tc_fence_after();
       if (elect_one_sync()) {
         constexpr uint32_t IDESC = make_idesc_bf16(TILE, C, 0, 0);
-        const uint32_t a_u32 = sm_u32 + OFF_A1, w_u32 = sm_u32 + OFF_W2;
+        const uint32_t a_u32 = sm_u32 + LT::OFF_A1, w_u32 = sm_u32 + LT::OFF_W2;
         // z2 decides the ReLU masks of the backward: three-term splits, six products (everything above 2^-24 |a w|), so
         // the recomputed masks flip no more often than an fp32 product's would
 #pragma unroll
@@ -357,14 +377,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
 
     // ================= epilogue 1 =======================================================================
     {
-      float v[16];
-      tmem_ld16(T_Z2 + ((uint32_t)(eq * 32) << 16) + (uint32_t)(ecg * 16), v);
+      float v[NCOL];
+      tmem_ldn(T_Z2 + ((uint32_t)(eq * 32) << 16) + (uint32_t)(ecg * NCOL), v);
       const bool valid = eslot < nvalid;
-      if (D1) {
+      if (!eact) {
+      } else if (D1) {
         // xhat2 with the ReLU mask in the lowest mantissa bit (a 1-ulp perturbation of a statistic's summand)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = ecg * 16 + k * 4;
+        for (int k = 0; k < NCOL / 4; ++k) {
+          const int c = ecg * NCOL + k * 4;
           const float4 is2 = *reinterpret_cast<const float4*>(tab + TB_IS2 * C + c), xm2 = *reinterpret_cast<const float4*>(tab + TB_XM2 * C + c);
           const float4 sc2 = *reinterpret_cast<const float4*>(tab + TB_SC2 * C + c), sh2 = *reinterpret_cast<const float4*>(tab + TB_SH2B * C + c);
           const float isv[4] = {is2.x, is2.y, is2.z, is2.w}, xmv[4] = {xm2.x, xm2.y, xm2.z, xm2.w};
@@ -377,16 +398,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
             const uint32_t m = fmaf(a, scv[q], shv[q]) > 0.f ? 1u : 0u;
             o[q] = __uint_as_float((__float_as_uint(xh) & ~1u) | m);
           }
-          *reinterpret_cast<float4*>(s_t + off_f(eslot, ecg * 4 + k)) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(s_t + off_f(eslot, ecg * (NCOL / 4) + k)) = make_float4(o[0], o[1], o[2], o[3]);
         }
       } else {
-        float dz[16];
+        float dz[NCOL];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = ecg * 16 + k * 4;
+        for (int k = 0; k < NCOL / 4; ++k) {
+          const int c = ecg * NCOL + k * 4;
           const float4 sc2 = *reinterpret_cast<const float4*>(tab + TB_SC2 * C + c), sh2 = *reinterpret_cast<const float4*>(tab + TB_SH2B * C + c);
           const float4 c0 = *reinterpret_cast<const float4*>(tab + TB_C0 * C + c), c1 = *reinterpret_cast<const float4*>(tab + TB_C1 * C + c);
-          const float4 gq = *reinterpret_cast<const float4*>(s_t + off_f(eslot, ecg * 4 + k));
+          const float4 gq = *reinterpret_cast<const float4*>(s_t + off_f(eslot, ecg * (NCOL / 4) + k));
           const float scv[4] = {sc2.x, sc2.y, sc2.z, sc2.w}, shv[4] = {sh2.x, sh2.y, sh2.z, sh2.w};
           const float c0v[4] = {c0.x, c0.y, c0.z, c0.w}, c1v[4] = {c1.x, c1.y, c1.z, c1.w};
           const float gvv[4] = {gq.x, gq.y, gq.z, gq.w};
@@ -398,11 +419,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
           }
         }
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < NCOL / 8; ++k) {
           uint2 h0, l0, h1, l1;
           split_bf16x4(make_float4(dz[k * 8], dz[k * 8 + 1], dz[k * 8 + 2], dz[k * 8 + 3]), h0, l0);
           split_bf16x4(make_float4(dz[k * 8 + 4], dz[k * 8 + 5], dz[k * 8 + 6], dz[k * 8 + 7]), h1, l1);
-          const uint32_t ob = off_bf(eslot, ecg * 16 + k * 8);
+          const uint32_t ob = off_bf(eslot, ecg * NCOL + k * 8);
           *reinterpret_cast<uint4*>(dz_t + ob) = make_uint4(h0.x, h0.y, h1.x, h1.y);
           *reinterpret_cast<uint4*>(dz_t + T_BF + ob) = make_uint4(l0.x, l0.y, l1.x, l1.y);
         }
@@ -418,8 +439,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
         tc_fence_after();
         if (elect_one_sync()) {
           constexpr uint32_t IDESC_NN = make_idesc_bf16(TILE, C, 0, 1);     // A K-major, B = W2 read MN-major
-          constexpr uint32_t IDESC_TN = make_idesc_bf16(TILE, C, 1, 1);     // both MN-major: contraction over the slots
-          const uint32_t a_u32 = sm_u32 + OFF_A1, d_u32 = sm_u32 + OFF_DZ, w_u32 = sm_u32 + OFF_W2;
+          constexpr uint32_t IDESC_TN = make_idesc_bf16(128, C, 1, 1);      // M = 128 = [dz2_hi ; dz2_lo]^T, both MN-major: contraction over the slots
+          const uint32_t a_u32 = sm_u32 + LT::OFF_A1, d_u32 = sm_u32 + LT::OFF_DZ, w_u32 = sm_u32 + LT::OFF_W2;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t a_hi = make_desc(d_u32 + ks * 32u, 16, 1024, LAYOUT_SW128);
@@ -432,7 +453,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
           }
           if (D2T) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
+            for (int ks = 0; ks < TILE / 16; ++ks) {
               const uint64_t a_st = make_desc(d_u32 + ks * 2048u, T_BF, 1024, LAYOUT_SW128);      // rows 0-63 hi, 64-127 lo
               const uint64_t b_hi = make_desc(a_u32 + ks * 2048u, 8192, 1024, LAYOUT_SW128);
               const uint64_t b_lo = make_desc(a_u32 + T_BF + ks * 2048u, 8192, 1024, LAYOUT_SW128);   // the mid part of a1
@@ -450,20 +471,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
 
       // ================= epilogue 2: dy1 = da1 mask1 (overwrites the thread's own G entries) ==============
       {
-        float v[16];
-        tmem_ld16(T_DA + ((uint32_t)(eq * 32) << 16) + (uint32_t)(ecg * 16), v);
+        float v[NCOL];
+        tmem_ldn(T_DA + ((uint32_t)(eq * 32) << 16) + (uint32_t)(ecg * NCOL), v);
         const bool valid = eslot < nvalid;
+        if (eact) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = ecg * 16 + k * 4;
+        for (int k = 0; k < NCOL / 4; ++k) {
+          const int c = ecg * NCOL + k * 4;
           const float4 sc1 = *reinterpret_cast<const float4*>(tab + TB_SC1 * C + c), sh1 = *reinterpret_cast<const float4*>(tab + TB_SH1 * C + c);
-          const float4 z = *reinterpret_cast<const float4*>(z_t + off_f(eslot, ecg * 4 + k));
+          const float4 z = *reinterpret_cast<const float4*>(z_t + off_f(eslot, ecg * (NCOL / 4) + k));
           float4 o;
           o.x = (valid && fmaf(z.x, sc1.x, sh1.x) > 0.f) ? v[k * 4 + 0] : 0.f;
           o.y = (valid && fmaf(z.y, sc1.y, sh1.y) > 0.f) ? v[k * 4 + 1] : 0.f;
           o.z = (valid && fmaf(z.z, sc1.z, sh1.z) > 0.f) ? v[k * 4 + 2] : 0.f;
           o.w = (valid && fmaf(z.w, sc1.w, sh1.w) > 0.f) ? v[k * 4 + 3] : 0.f;
-          *reinterpret_cast<float4*>(s_t + off_f(eslot, ecg * 4 + k)) = o;
+          *reinterpret_cast<float4*>(s_t + off_f(eslot, ecg * (NCOL / 4) + k)) = o;
+        }
         }
       }
       tc_fence_before();
@@ -577,19 +600,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
   // ================= per-CTA partials (fixed order, no atomics) ============================================
   if (D2T) {
     // dW2 accumulator [128 = hi | lo rows of dz2^T][64]
-    float v[16];
-    if (ntiles > 0) tmem_ld16(T_DW + ((uint32_t)(eq * 32) << 16) + (uint32_t)(ecg * 16), v);
+    float v[NCOL];
+    if (ntiles > 0) tmem_ldn(T_DW + ((uint32_t)(eq * 32) << 16) + (uint32_t)(ecg * NCOL), v);
     else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      for (int i = 0; i < NCOL; ++i) v[i] = 0.f;
     }
-    float* o = p.part_w2 + ((int64_t)blockIdx.x * 128 + eslot) * C + ecg * 16;
+    float* o = p.part_w2 + ((int64_t)blockIdx.x * 128 + eq * 32 + lane) * C + ecg * NCOL;
 #pragma unroll
-    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    for (int i = 0; i < NCOL; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
   }
   if (MODE != M_D2S) {
     constexpr int NV = D2T ? 48 : 16;
-    float* red = reinterpret_cast<float*>(sm);                  // [64 rl][8 k8][NV], aliases the operand tiles
+    float* red = reinterpret_cast<float*>(sm);                  // [THREADS / 8 rl][8 k8][NV], aliases the operand tiles
     float* mine = red + (size_t)(rl * 8 + k8) * NV;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { mine[i] = acc_a[i]; mine[8 + i] = acc_b[i]; }
@@ -598,27 +621,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_edge_bwd(const Params p) {
       for (int i = 0; i < 32; ++i) mine[16 + i] = acc_t[D2T ? i : 0];
     }
     __syncthreads();
-    if (tid < 8 * NV) {
-      const int kk = tid / NV, vv = tid % NV;
+    for (int tt = tid; tt < 8 * NV; tt += THREADS) {
+      const int kk = tt / NV, vv = tt % NV;
       float s = 0.f;
-      for (int q = 0; q < 64; ++q) s += red[(size_t)(q * 8 + kk) * NV + vv];
+      for (int q = 0; q < THREADS / 8; ++q) s += red[(size_t)(q * 8 + kk) * NV + vv];
       const int i = vv < 16 ? (vv & 7) : (vv - 16) >> 2;
       const int c = (i < 4) ? 4 * kk + i : 32 + 4 * kk + (i - 4);
       if (vv < 16) p.part[((int64_t)blockIdx.x * 2 + (vv >> 3)) * C + c] = s;
       else p.part_t[(int64_t)blockIdx.x * (C * 4) + c * 4 + ((vv - 16) & 3)] = s;
     }
   } else {
-    float* red2 = reinterpret_cast<float*>(sm);                 // [32 sl][16 gc][20]
+    float* red2 = reinterpret_cast<float*>(sm);                 // [SLG sl][16 gc][20]
     float* m2 = red2 + (size_t)(sl * 16 + gc) * 20;
 #pragma unroll
     for (int i = 0; i < 16; ++i) m2[i] = acc_tx[TXA ? i : 0];
 #pragma unroll
     for (int k = 0; k < 4; ++k) m2[16 + k] = acc_sa[TXA ? k : 0];
     __syncthreads();
-    if (tid < 16 * 20) {
-      const int g2 = tid / 20, vv = tid % 20;
+    for (int tt = tid; tt < 16 * 20; tt += THREADS) {
+      const int g2 = tt / 20, vv = tt % 20;
       float s = 0.f;
-      for (int q = 0; q < 32; ++q) s += red2[(size_t)(q * 16 + g2) * 20 + vv];
+      for (int q = 0; q < SLG; ++q) s += red2[(size_t)(q * 16 + g2) * 20 + vv];
       float* o = p.part_t + (int64_t)blockIdx.x * (C * 4 + 4);
       if (vv < 16) o[(4 * g2 + (vv >> 2)) * 4 + (vv & 3)] = s;
       else if (g2 == 0) o[C * 4 + (vv - 16)] = s;
@@ -697,23 +720,40 @@ __global__ void __launch_bounds__(256) k_edge_bwd_combine(
   }
 }
 
-template <int MODE>
-static cudaError_t launch(const Params& p, int grid, cudaStream_t st) {
+template <int MODE, int TILE>
+static cudaError_t launch_t(const Params& p, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_edge_bwd<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_edge_bwd<MODE, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L<TILE>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  k_edge_bwd<MODE><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+  k_edge_bwd<MODE, TILE><<<grid, L<TILE>::THREADS, L<TILE>::SMEM_BYTES, st>>>(p);
   return cudaSuccess;
+}
+
+// YOLAT_EB_TILE=128 selects one 512-thread CTA per SM over 128-slot tiles; default: two 256-thread CTAs over 64-slot tiles
+static int tile_slots() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("YOLAT_EB_TILE");
+    v = (e && atoi(e) == 128) ? 128 : 64;
+  }
+  return v;
+}
+
+template <int MODE>
+static cudaError_t launch(const Params& p, int grid, cudaStream_t st) {
+  return tile_slots() == 128 ? launch_t<MODE, 128>(p, grid, st) : launch_t<MODE, 64>(p, grid, st);
 }
 
 }  // namespace eb
 
 int edge_bwd_grid(int64_t E) {
-  const int64_t tiles = cdiv(E > 0 ? E : 1, eb::TILE);
-  return (int)(tiles < (int64_t)kNumSMs ? tiles : (int64_t)kNumSMs);
+  const int tile = eb::tile_slots();
+  const int64_t tiles = cdiv(E > 0 ? E : 1, tile);
+  const int64_t cap = (int64_t)kNumSMs * (tile == 64 ? 2 : 1);       // persistent: every resident CTA owns one slot range
+  return (int)(tiles < cap ? tiles : cap);
 }
 
 // Workspace of the fused edge backward, in floats (all taken from `ws` in this order).

@@ -76,6 +76,10 @@ class OverlappedGradSync(object):
       are captured into the step graph -- reduces the remaining head of the buffer, joins both collectives and scales
       by 1 / world.  Only that second, small all-reduce is exposed.
 
+    `overlap=False` drops the hooks: one collective over the whole buffer in `finish()` -- the variant to capture in a
+    CUDA graph (asynchronous NCCL work issued from autograd hooks inside a capture hung on torch 2.11 / NCCL 2.28;
+    tools/nccl_capture_probe.py lists what captures cleanly).
+
     BatchNorm statistics stay rank-local (DDP-default semantics).  Gradients must be re-created every step
     (`zero_grad(set_to_none=True)`, what GraphedStep does): an existing `p.grad` makes autograd accumulate in place
     instead of adopting the view.  If autograd ever declines a view (verified on every eager step), the object falls
