@@ -137,3 +137,24 @@ def test_unfused_backbone_signature():
         pooled, out_super2 = model.cls_net.forward_pooled(b.x, [b.edge.T], [None], [b.e_attr], Segments(b.bbox_idx, 40))
         assert max_rel(scatter(out_feat, b.bbox_idx, dim=0, reduce='max'), pooled) < 1e-6
         assert torch.equal(out_super, out_super2)
+
+
+def test_out_of_range_edges_are_reported_on_request():
+    """An edge endpoint outside [0, N) makes the reference fail (index error in PyG's gather).  The graph build counts
+    such edges on the device; `check_graph` (YOLAT_CHECK_GRAPH=1, always on inside predict()) turns the count into an
+    exception at the cost of one host sync."""
+    from yolat_vectorgraphicsrecognition_b200 import synth, _lib
+    from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
+    opt = synth.make_opt(n_classes=17)
+    torch.manual_seed(0)
+    model = arch.SparseCADGCN(opt).cuda().eval()
+    b = synth.floorplans_batch(graphs=1, n=320, e=1200, seed=4).to('cuda')
+    b.edge = b.edge.clone()
+    b.edge[7, 0] = b.x.shape[0] + 5
+    model.check_graph = True
+    with pytest.raises(_lib.YolatError, match='outside'):
+        with torch.no_grad():
+            model(b, None)
+    model.check_graph = False
+    with torch.no_grad():
+        assert torch.isfinite(model(b, None)[0]).all()      # dropped silently when nobody asks (no sync on the hot path)

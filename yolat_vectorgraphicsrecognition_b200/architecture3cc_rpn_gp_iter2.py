@@ -120,6 +120,9 @@ class SparseCADGCN(torch.nn.Module):
         self.class_specific = opt.class_specific
         self.dim_stat = 0
 
+        import os
+        self.check_graph = os.environ.get('YOLAT_CHECK_GRAPH', '0') not in ('', '0')
+        self._in_predict = False
         self.cls_net = Backbone(opt)
         self.prediction_cls = MultiSeq(*[
             MLP([(self.cls_net.fusion_dims + 1024) * 2 + self.dim_stat, 512], act, norm, bias),
@@ -153,7 +156,10 @@ class SparseCADGCN(torch.nn.Module):
         e_attr = _dev(data.e_attr, dev)
         # stat_feats is copied by the reference (:112) but unused (dim_stat = 0, :87): not moved here.
 
-        graph = CSRGraph(edge.T, x.shape[0])                   # edges = [data.edge.cuda().T]  (:110)
+        # edges = [data.edge.cuda().T]  (:110).  Edge endpoints outside [0, N) make the reference fail (index error in PyG's
+        # gather, KeyError in build_data); the graph build counts them on the device, and the count is read back -- one
+        # host sync -- wherever a sync exists anyway (predict) or when `check_graph` is set (YOLAT_CHECK_GRAPH=1).
+        graph = CSRGraph(edge.T, x.shape[0], check=self.check_graph or self._in_predict)
         seg = Segments(bbox_idx, pred_bbox.shape[0])           # one proposal per bbox row: no index.max() sync
         pooled, out_feat_cls_super = self.cls_net.forward_pooled(x, [graph], [None], [e_attr], seg)   # :121-122
         out_feat_cls = torch.cat([pooled, out_feat_cls_super], dim=1)                                  # :127
@@ -228,6 +234,13 @@ class SparseCADGCN(torch.nn.Module):
             slice_image_bbox_root.append(len(root_nodes))
         dd = self._device_data(data)
         nd, slice_bbox = self._build_data_device(dd, root_nodes, slices)
+        self._in_predict = True          # forward() verifies the edge endpoints: predict syncs with the host anyway
+        try:
+            return self._predict_stages(dd, nd, slice_bbox, slices, roots, slice_root, slice_image_bbox_root)
+        finally:
+            self._in_predict = False
+
+    def _predict_stages(self, dd, nd, slice_bbox, slices, roots, slice_root, slice_image_bbox_root):
         pred_cls, pred_bbox = self.forward(nd, slices)
 
         _, is_object = pred_cls.max(1)

@@ -666,7 +666,7 @@ __global__ void k_edge_bwd_records(const int32_t* __restrict__ src_t, const int3
 }
 
 // Node-level tail of the backward (see the header): dW2, dW1c and dP | dQ from the per-CTA partials and row sums.
-//   blocks [0, nb_pq): rows of dpq;  then 16 blocks: dW2;  last block: dW1c.
+//   blocks [0, nb_pq): rows of dpq;  then 64 blocks: dW2;  last block: dW1c.
 __global__ void __launch_bounds__(256) k_edge_bwd_combine(
     int64_t N, int nb_pq, const float* __restrict__ Ut, const float* __restrict__ Xt, const float* __restrict__ Us,
     const float* __restrict__ Xs, const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ rowptr_s,
@@ -698,13 +698,19 @@ __global__ void __launch_bounds__(256) k_edge_bwd_combine(
     return;
   }
   const int b = (int)blockIdx.x - nb_pq;
-  if (b < 16) {
+  if (b < 64) {
+    // dW2[o][i] = sum over CTAs of (hi rows + lo rows): block = 64 outputs x 4 slices of the CTA range, fixed summation order
     if (!dw2) return;
-    const int idx = b * 256 + tid, o = idx >> 6, i = idx & 63;
+    __shared__ float red[4][64];
+    const int lo = tid & 63, sl = tid >> 6;
+    const int idx = b * 64 + lo, o = idx >> 6, i = idx & 63;
+    const int per = (grid2 + 3) / 4, k0 = sl * per, k1 = min(grid2, k0 + per);
     float s = 0.f;
-    for (int k = 0; k < grid2; ++k)
+    for (int k = k0; k < k1; ++k)
       s += part_w2[((int64_t)k * 128 + o) * C + i] + part_w2[((int64_t)k * 128 + 64 + o) * C + i];
-    dw2[idx] = s;
+    red[sl][lo] = s;
+    __syncthreads();
+    if (sl == 0) dw2[idx] = (red[0][lo] + red[1][lo]) + (red[2][lo] + red[3][lo]);
     return;
   }
   if (!dw1c) return;
@@ -732,12 +738,15 @@ static cudaError_t launch_t(const Params& p, int grid, cudaStream_t st) {
   return cudaSuccess;
 }
 
-// YOLAT_EB_TILE=128 selects one 512-thread CTA per SM over 128-slot tiles; default: two 256-thread CTAs over 64-slot tiles
+// Default: one 512-thread CTA per SM over 128-slot tiles.  YOLAT_EB_TILE=64 selects two 256-thread CTAs per SM over 64-slot
+// tiles -- measured no faster (N = 320 000: D1 321 / D2T 603 / D2S 480 us vs 330 / 585 / 456; step 1.50 vs 1.46 ms): the
+// passes are bound by their instruction count (296 M warp instructions for D2T, profiles/r2_c_bwd_*), not by the
+// latencies a second resident CTA would hide, and the M = 64 accumulators idle half of every epilogue warp.
 static int tile_slots() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("YOLAT_EB_TILE");
-    v = (e && atoi(e) == 128) ? 128 : 64;
+    v = (e && atoi(e) == 64) ? 64 : 128;
   }
   return v;
 }
@@ -832,7 +841,7 @@ int edge_bwd_fused(const GraphView& g, int64_t N, int64_t E, const float* pq, in
   }
   YOLAT_TRY(bn_bwd_finalize(w.part2, grid, E, C, stat1, gamma1, 1, w.bstat1, dg1, dbe1, db1, st));
   const int nb_pq = (int)(cdiv(N, 8) < 592 ? cdiv(N, 8) : 592);
-  k_edge_bwd_combine<<<nb_pq + 17, 256, 0, st>>>(N, nb_pq, w.Ut, w.Xt, w.Us, w.Xs, g.rowptr_t, g.rowptr_s, stat1, w.bstat1,
+  k_edge_bwd_combine<<<nb_pq + 65, 256, 0, st>>>(N, nb_pq, w.Ut, w.Xt, w.Us, w.Xs, g.rowptr_t, g.rowptr_s, stat1, w.bstat1,
                                                  w.part_w2, grid, w.part_T, w.part_tx, grid, dpq, dw2, dw1c);
   YOLAT_CHECK_LAUNCH();
   return YOLAT_OK;
