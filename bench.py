@@ -45,6 +45,9 @@ def parse():
     ap.add_argument('--graphs', type=int, default=0, help='graphs per rank per step (0 = the workload default)')
     ap.add_argument('--global-batch', type=int, default=0,
                     help='BASELINE config 4: total graphs per step, split across the ranks (strong scaling)')
+    ap.add_argument('--collective', choices=('overlap', 'single'), default='overlap',
+                    help='N > 1: overlap = head-bucket all-reduce under the backward + the remainder after it; single = one '
+                         'all-reduce after the backward')
     ap.add_argument('--mode', default='graph', choices=['graph', 'eager'],
                     help='graph: the step is replayed as one CUDA graph (GraphedStep); eager: launched from Python')
     ap.add_argument('--cpu-steps', type=int, default=8, help='timed steps of the cpu_baseline leg')
@@ -226,10 +229,12 @@ def main():
     resident = host.to(dev)
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
     # N > 1: gradients live in one flat buffer written by the backward kernels (no gather copy before the collective).
-    # Eager steps all-reduce the classifier head's 5.3 MB from an autograd hook while the rest of the backward runs and
-    # the remaining 1.1 MB after it; a step captured in a CUDA graph reduces the whole buffer with ONE collective at the
-    # end of the backward (asynchronous NCCL work issued from hooks inside a capture hung on this torch / NCCL stack).
-    sync = dp.OverlappedGradSync(model, overlap=args.mode == 'eager') if world > 1 else None
+    # The classifier head's 5.3 MB are all-reduced from an autograd hook while the rest of the backward runs, the
+    # remaining 1.1 MB after it.  In the captured step the hook issues the collective on a forked side stream (a parallel
+    # branch of the step graph); --collective single reduces the whole buffer once at the end of the backward.
+    sync = None
+    if world > 1:
+        sync = dp.OverlappedGradSync(model, overlap=args.collective == 'overlap', side_stream=args.mode == 'graph')
 
     def eager_step(batch):
         for p in params:
@@ -300,7 +305,7 @@ def main():
         ms_plain = timed(plain, resident, args.steps)
         sync.enabled = True
         collective = {'op': 'ncclAllReduce(sum) of the flat fp32 gradient buffer (written in place by the backward kernels), '
-                            'captured in the step graph',
+                            'captured in the step graph; schedule: %s' % args.collective,
                       'bytes': 4 * sync.numel, 'overlapped_bytes': sync.overlapped_bytes,
                       'exposed_bytes': sync.exposed_bytes, 'exposed_us': (ms - ms_plain) * 1e3,
                       'ms_per_step_without_collective': ms_plain, 'views_adopted': not sync.copy_mode}
@@ -437,7 +442,11 @@ def main():
         flush.zero_()
         torch.cuda.synchronize()
         lib.yolat_prof_enable(1)
+        if sync is not None:
+            sync.enabled = False      # rank 0 only from here on: no collective may be issued
         eager_step(resident)
+        if sync is not None:
+            sync.enabled = True
         torch.cuda.synchronize()
         lib.yolat_prof_enable(0)
         roof['at_step_size'] = {'what': 'per-launch averages inside one eager step of the timed workload '
@@ -516,9 +525,22 @@ def main():
             'launch_mode': args.mode,
             'other_mode': {'mode': 'eager' if args.mode == 'graph' else 'graph', 'ms_per_step': ms_other},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear-down order matters: the captured NCCL kernels keep the communicator referenced until their graphs are
+        # destroyed.  The line above is already out; if the communicator still refuses to go, leave without it.
+        import threading
+        sys.stdout.flush()
+        sys.stderr.flush()
+        bail = threading.Timer(20.0, lambda: os._exit(0))
+        bail.daemon = True
+        bail.start()
+        barrier()
+        graphed.release()
+        if sync is not None:
+            sync.close()
         dist.destroy_process_group()
+        bail.cancel()
 
 
 if __name__ == '__main__':

@@ -20,7 +20,9 @@ def _free_port():
 
 
 def _worker(rank, world, port, out):
+    import faulthandler
     import torch.distributed as dist
+    faulthandler.dump_traceback_later(150, exit=True)     # a stalled collective dumps every thread's stack and exits
     from yolat_vectorgraphicsrecognition_b200 import synth, dp
     from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
     from yolat_vectorgraphicsrecognition_b200.graphed import GraphedStep
@@ -61,19 +63,50 @@ def _worker(rank, world, port, out):
         torch.cuda.synchronize()
         err_graph = float((sync.flat - want).abs().max() / want.abs().max())
         adopted = all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(sync.params, sync.views))
-        if rank == 0:
-            torch.save(dict(err_eager=err_eager, err_graph=err_graph, adopted=adopted, overlapped=overlapped, total=total), out)
         sync.close()
+        step.release()                # captured NCCL work keeps the communicator referenced: drop the graphs first
+        del step
+        # ... and the overlapped schedule captured: the hook forks a side stream for the head bucket (a parallel branch
+        # of the step graph), finish() joins it
+        sync = dp.OverlappedGradSync(model, side_stream=True)
+        step = GraphedStep(model, crit, extra=sync.finish)
+        step(shards[rank])
+        step(shards[rank])
+        torch.cuda.synchronize()
+        err_side = float((sync.flat - want).abs().max() / want.abs().max())
+        adopted = adopted and all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(sync.params, sync.views))
+        if rank == 0:
+            torch.save(dict(err_eager=err_eager, err_graph=err_graph, err_side=err_side, adopted=adopted,
+                            overlapped=overlapped, total=total), out)
+        sync.close()
+        step.release()
+        del step
+    except BaseException:
+        import traceback
+        with open('%s.err%d' % (out, rank), 'w') as f:
+            f.write(traceback.format_exc())
+        raise
     finally:
+        torch.cuda.synchronize()
+        faulthandler.cancel_dump_traceback_later()
+        faulthandler.dump_traceback_later(30, exit=True)
         dist.destroy_process_group()
+        faulthandler.cancel_dump_traceback_later()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
 def test_overlapped_grad_sync_nccl_world2(tmp_path):
     import torch.multiprocessing as mp
     out = str(tmp_path / 'res.pt')
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    try:
+        mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    except Exception:
+        import glob
+        for f in glob.glob(out + '.err*'):
+            print(f, open(f).read())
+        if not os.path.exists(out):
+            raise
     res = torch.load(out)
     assert res['adopted']
-    assert res['err_eager'] < 1e-6 and res['err_graph'] < 1e-6, res
+    assert res['err_eager'] < 1e-6 and res['err_graph'] < 1e-6 and res['err_side'] < 1e-6, res
     assert res['overlapped'] > 0.8 * res['total']

@@ -18,6 +18,7 @@
 //     (double-buffered shared memory);
 //   * epilogue: tcgen05.ld TMEM -> registers -> padded shared tile -> coalesced stores (+bias, +accumulate),
 //     optional per-tile column sum / sum-of-squares partials (BatchNorm statistics without re-reading z).
+#include <cuda.h>
 #include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
@@ -440,7 +441,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const Params p) {
 //   warps 9..12 epilogue: tcgen05.ld (lane quarter = warp & 3) -> bias / accumulate -> direct 128-byte row stores, or
 //               split-K partial tiles; per-warp column statistics through a private 32 x 33 transpose tile.
 // The epilogue of tile i overlaps the main loop of tile i+1, which the one-tile-per-CTA kernel above cannot do.
-constexpr int WS_PRODUCERS = 8, WS_THREADS = (WS_PRODUCERS + 1 + 4) * 32;
+//
+// TMA variant (template flag TMA): a 14th warp issues cp.async.bulk.tensor loads of the raw fp32 k-blocks straight into
+// the stage's `hi` buffers (the tensor maps are encoded with the swizzle mode the UMMA descriptors expect: SWIZZLE_128B
+// for K-major operands, SWIZZLE_128B_ATOM_32B for 32-bit MN-major ones; out-of-range rows / reduction tails arrive as
+// zeros), and warps 0..7 become converters: they wait for the bytes, split every 16-byte chunk IN PLACE (hi back to
+// where it was, lo into the neighbouring buffer -- elementwise, so the swizzle never has to be undone) and hand the
+// stage to the MMA warp.  No global load passes through registers; the loads of NST k-blocks are in flight per CTA.
+constexpr int WS_PRODUCERS = 8, WS_THREADS = (WS_PRODUCERS + 1 + 4) * 32, WS_THREADS_TMA = WS_THREADS + 32;
+struct alignas(64) TmaMaps { CUtensorMap a, b; };
 template <int BN> struct WsCfg {
   static constexpr int NST = (BN == 128) ? 3 : 4;
   static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * BN * 128;
@@ -448,8 +457,9 @@ template <int BN> struct WsCfg {
   static constexpr size_t SMEM = (size_t)NST * STAGE_BYTES + XPOSE_BYTES + 1024;
 };
 
-template <int MODE, int BN, bool FAST>
-__global__ void __launch_bounds__(WS_THREADS, 1) k_tc_gemm_ws(const Params p, const int gn, const int gm, const int ksplit) {
+template <int MODE, int BN, bool FAST, bool TMA>
+__global__ void __launch_bounds__(TMA ? WS_THREADS_TMA : WS_THREADS, 1)
+k_tc_gemm_ws(const Params p, const int gn, const int gm, const int ksplit, const __grid_constant__ TmaMaps maps) {
   using Cfg = WsCfg<BN>;
   constexpr int NST = Cfg::NST;
   constexpr uint32_t B_BYTES = BN * 128;
@@ -459,7 +469,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_tc_gemm_ws(const Params p, co
   constexpr uint32_t IDESC = make_idesc(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_full[NST], bar_empty[NST], bar_acc_full[2], bar_acc_empty[2];
+  __shared__ uint64_t bar_full[NST], bar_empty[NST], bar_acc_full[2], bar_acc_empty[2], bar_tma[NST];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -467,6 +477,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_tc_gemm_ws(const Params p, co
   uint8_t* tiles = smem_raw + pad;
   const uint32_t tiles_u32 = raw_u32 + pad;
   float* xpose = reinterpret_cast<float*>(tiles + NST * STAGE_BYTES);
+  // MN-major operands staged by TMA: one 32 x 32 box per 32 output indices => [mn_atom][k_atom (8)][4 k-rows][128 B]
+  // (the register loaders keep the k-atom outermost); only the two strides of the descriptor differ.
+  constexpr uint32_t A_LBO = TMA ? 4096u : 512u, A_SBO = TMA ? 512u : (uint32_t)(BM / 32 * 512);
+  constexpr uint32_t B_LBO = TMA ? 4096u : 512u, B_SBO = TMA ? 512u : (uint32_t)(BN / 32 * 512);
+  constexpr uint32_t A_KSTEP = TMA ? 1024u : (uint32_t)(BM / 32 * 1024), B_KSTEP = TMA ? 1024u : (uint32_t)(BN / 32 * 1024);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int total = gn * gm * ksplit;
@@ -476,6 +491,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_tc_gemm_ws(const Params p, co
     for (int i = 0; i < NST; ++i) {
       mbar_init(smem_u32(&bar_full[i]), WS_PRODUCERS * 32);
       mbar_init(smem_u32(&bar_empty[i]), 1);
+      mbar_init(smem_u32(&bar_tma[i]), 1);
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -502,7 +518,63 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_tc_gemm_ws(const Params p, co
     c.nkb = (int)((c.kend - c.kbeg + BK - 1) / BK);
   };
 
-  if (warp < WS_PRODUCERS) {
+  if (TMA && warp < WS_PRODUCERS) {
+    // =========================== converters (TMA variant) ================================================
+    Cur s;
+    load_tile(blockIdx.x, s);
+    int st = 0;
+    uint32_t use = 0;
+    while (s.tile < total) {
+      mbar_wait(smem_u32(&bar_tma[st]), use & 1u);            // the raw fp32 k-block of A and B has landed
+      uint8_t* sp = tiles + (uint32_t)st * STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < (int)(A_BYTES / 16) / (WS_PRODUCERS * 32); ++i) {
+        const uint32_t off = (uint32_t)(tid + i * WS_PRODUCERS * 32) * 16u;
+        store_split_fast(sp, sp + A_BYTES, off, *reinterpret_cast<const float4*>(sp + off));
+      }
+#pragma unroll
+      for (int i = 0; i < (int)(B_BYTES / 16) / (WS_PRODUCERS * 32); ++i) {
+        const uint32_t off = (uint32_t)(tid + i * WS_PRODUCERS * 32) * 16u;
+        store_split_fast(sp + 2 * A_BYTES, sp + 2 * A_BYTES + B_BYTES, off,
+                         *reinterpret_cast<const float4*>(sp + 2 * A_BYTES + off));
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&bar_full[st]));
+      if (++st == NST) { st = 0; ++use; }
+      if (++s.kb >= s.nkb) load_tile(s.tile + gridDim.x, s);
+    }
+  } else if (TMA && warp == WS_PRODUCERS + 5) {
+    // =========================== TMA issue (TMA variant) =================================================
+    if (lane == 0) { tma_prefetch_desc(&maps.a); tma_prefetch_desc(&maps.b); }
+    Cur f;
+    load_tile(blockIdx.x, f);
+    int st = 0;
+    uint32_t use = 0;
+    while (f.tile < total) {
+      if (use > 0) mbar_wait(smem_u32(&bar_empty[st]), (use - 1) & 1u);     // the MMAs that read this stage are done
+      if (elect_one_sync()) {
+        const uint32_t bar = smem_u32(&bar_tma[st]);
+        const uint32_t sa = tiles_u32 + (uint32_t)st * STAGE_BYTES, sb = sa + 2 * A_BYTES;
+        const int32_t k0 = (int32_t)(f.kbeg + (int64_t)f.kb * BK);
+        mbar_expect_tx(bar, A_BYTES + B_BYTES);
+        if (A_MN) {
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + (uint32_t)j * 4096u, &maps.a, f.m0 + 32 * j, k0, bar);
+        } else {
+          tma_load_2d(sa, &maps.a, k0, f.m0, bar);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + (uint32_t)j * 4096u, &maps.b, f.n0 + 32 * j, k0, bar);
+        } else {
+          tma_load_2d(sb, &maps.b, k0, f.n0, bar);
+        }
+      }
+      __syncwarp();
+      if (++st == NST) { st = 0; ++use; }
+      if (++f.kb >= f.nkb) load_tile(f.tile + gridDim.x, f);
+    }
+  } else if (warp < WS_PRODUCERS) {
     // =========================== producers ===============================================================
     typename Loaders<MODE, BN>::ALoad la[2];
     typename Loaders<MODE, BN>::BLoad lb[2];
@@ -570,15 +642,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_tc_gemm_ws(const Params p, co
           const uint32_t sb = sa + 2 * A_BYTES;
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
-            const uint32_t a_off = A_MN ? (uint32_t)ks * (BM / 32 * 1024) : (uint32_t)ks * 32u;
-            const uint32_t b_off = B_MN ? (uint32_t)ks * (BN / 32 * 1024) : (uint32_t)ks * 32u;
-            const uint64_t a_hi = A_MN ? make_desc(sa + a_off, 512, BM / 32 * 512, LAYOUT_SW128_BASE32B)
+            const uint32_t a_off = A_MN ? (uint32_t)ks * A_KSTEP : (uint32_t)ks * 32u;
+            const uint32_t b_off = B_MN ? (uint32_t)ks * B_KSTEP : (uint32_t)ks * 32u;
+            const uint64_t a_hi = A_MN ? make_desc(sa + a_off, A_LBO, A_SBO, LAYOUT_SW128_BASE32B)
                                        : make_desc(sa + a_off, 16, 1024, LAYOUT_SW128);
-            const uint64_t a_lo = A_MN ? make_desc(sa + A_BYTES + a_off, 512, BM / 32 * 512, LAYOUT_SW128_BASE32B)
+            const uint64_t a_lo = A_MN ? make_desc(sa + A_BYTES + a_off, A_LBO, A_SBO, LAYOUT_SW128_BASE32B)
                                        : make_desc(sa + A_BYTES + a_off, 16, 1024, LAYOUT_SW128);
-            const uint64_t b_hi = B_MN ? make_desc(sb + b_off, 512, BN / 32 * 512, LAYOUT_SW128_BASE32B)
+            const uint64_t b_hi = B_MN ? make_desc(sb + b_off, B_LBO, B_SBO, LAYOUT_SW128_BASE32B)
                                        : make_desc(sb + b_off, 16, 1024, LAYOUT_SW128);
-            const uint64_t b_lo = B_MN ? make_desc(sb + B_BYTES + b_off, 512, BN / 32 * 512, LAYOUT_SW128_BASE32B)
+            const uint64_t b_lo = B_MN ? make_desc(sb + B_BYTES + b_off, B_LBO, B_SBO, LAYOUT_SW128_BASE32B)
                                        : make_desc(sb + B_BYTES + b_off, 16, 1024, LAYOUT_SW128);
             umma_tf32(d, a_lo, b_hi, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
             umma_tf32(d, a_hi, b_lo, IDESC, 1u);
@@ -591,7 +663,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_tc_gemm_ws(const Params p, co
         if (++st == NST) { st = 0; ++use; }
       }
     }
-  } else {
+  } else if (warp <= WS_PRODUCERS + 4) {
     // =========================== epilogue ================================================================
     const int q4 = warp & 3;                       // TMEM lane quarter this warp may read
     float* xp = xpose + (warp - WS_PRODUCERS - 1) * (32 * 33);
@@ -684,27 +756,84 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_tc_gemm_ws(const Params p, co
   if (warp == WS_PRODUCERS) tmem_dealloc(tmem_d, 2 * BN);
 }
 
-template <int MODE, int BN, bool FAST>
-static cudaError_t launch_ws2(const Params& p, int gn, int gm, int ksplit, cudaStream_t st) {
+template <int MODE, int BN, bool FAST, bool TMA>
+static cudaError_t launch_ws2(const Params& p, int gn, int gm, int ksplit, const TmaMaps& maps, cudaStream_t st) {
   constexpr size_t smem = WsCfg<BN>::SMEM;
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
-        cudaFuncSetAttribute(k_tc_gemm_ws<MODE, BN, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_tc_gemm_ws<MODE, BN, FAST, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int total = gn * gm * ksplit;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  k_tc_gemm_ws<MODE, BN, FAST><<<grid, WS_THREADS, smem, st>>>(p, gn, gm, ksplit);
+  k_tc_gemm_ws<MODE, BN, FAST, TMA><<<grid, TMA ? WS_THREADS_TMA : WS_THREADS, smem, st>>>(p, gn, gm, ksplit, maps);
   return cudaSuccess;
 }
+
+// ---- tensor maps ----------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; it is looked up through the runtime so the library keeps linking
+// against cudart only.  One 2-D fp32 map per operand: dim0 = the contiguous index, dim1 = the strided one.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// `base[outer * ld + inner]`, inner in [0, n_inner), outer in [0, n_outer); box = 32 inner x box_outer.
+static bool encode_map(CUtensorMap* m, const float* base, int64_t ld, int64_t n_inner, int64_t n_outer, int box_outer,
+                       bool mn_major) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)n_inner, (cuuint64_t)n_outer};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4u};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// YOLAT_TC_TMA: unset / "all" = every mode, "nt" | "nn" | "tn" (comma-separated) = those modes only, "0" = off.
+static bool tma_mode_enabled(int mode) {
+  static const int mask = [] {
+    const char* e = getenv("YOLAT_TC_TMA");
+    if (!e || !e[0] || e[0] == 'a') return 7;
+    if (e[0] == '0') return 0;
+    int m = 0;
+    for (const char* c = e; *c; ++c) {
+      if (c[0] == 'n' && c[1] == 't') m |= 1 << GEMM_NT;
+      if (c[0] == 'n' && c[1] == 'n') m |= 1 << GEMM_NN;
+      if (c[0] == 't' && c[1] == 'n') m |= 1 << GEMM_TN;
+    }
+    return m;
+  }();
+  return (mask >> mode) & 1;
+}
+
 template <int MODE, int BN>
 static cudaError_t launch_ws(const Params& p, int gn, int gm, int ksplit, cudaStream_t st) {
   // fast loaders: aligned vector loads on both operands and no partial 16-byte chunk along the contiguous dimension
   const bool a_k = (MODE != GEMM_TN), b_k = (MODE == GEMM_NT);      // operand contiguous along K?
+  TmaMaps maps{};
+  // TMA-fed variant: no operand prologue, 16-byte aligned bases and row pitches (the box handles every ragged edge)
+  if (tma_mode_enabled(MODE) && p.a_vec && p.b_vec && !p.a_sc && !p.b_sc && p.K < (1ll << 31)) {
+    const bool ok_a = a_k ? encode_map(&maps.a, p.A, p.lda, p.K, p.M, BM, false) : encode_map(&maps.a, p.A, p.lda, p.M, p.K, 32, true);
+    const bool ok_b = b_k ? encode_map(&maps.b, p.B, p.ldb, p.K, p.N, BN, false) : encode_map(&maps.b, p.B, p.ldb, p.N, p.K, 32, true);
+    if (ok_a && ok_b) return launch_ws2<MODE, BN, true, true>(p, gn, gm, ksplit, maps, st);
+  }
   const bool fast = p.a_vec && p.b_vec && ((a_k ? p.K : (int64_t)p.M) % 4 == 0) && ((b_k ? p.K : (int64_t)p.N) % 4 == 0);
-  return fast ? launch_ws2<MODE, BN, true>(p, gn, gm, ksplit, st) : launch_ws2<MODE, BN, false>(p, gn, gm, ksplit, st);
+  return fast ? launch_ws2<MODE, BN, true, false>(p, gn, gm, ksplit, maps, st)
+              : launch_ws2<MODE, BN, false, false>(p, gn, gm, ksplit, maps, st);
 }
 
 template <int MODE, int BN>
@@ -805,7 +934,7 @@ static int gemm_tc(const GemmArgs& a, GemmMode mode, Arena& ws, float* stat_part
   YOLAT_CHECK_LAUNCH();
   if (pl.ksplit > 1) {
     const int64_t tot = (int64_t)a.M * a.N;
-    if (pl.ksplit >= 16) {
+    if (pl.ksplit >= 16 && tot * 4 <= (int64_t)pl.ksplit * 16384) {   // few outputs per split: one block per 32 outputs
       k_splitk_sum_deep<<<(unsigned)cdiv(tot, 32), dim3(32, 32), 0, st>>>(part, pl.ksplit, a.M, a.N, a.bias, a.C, a.ldc,
                                                                           a.accumulate);
     } else {

@@ -86,6 +86,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar)
                : "memory");
 }
+// ---- TMA tensor copy (cp.async.bulk.tensor, 2-D tiled): one box of a tensor map -> shared, bytes counted on an mbarrier.
+// The box lands in the swizzle mode the map was encoded with; elements outside the tensor arrive as zeros and still count.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, int32_t c0, int32_t c1, uint32_t mbar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst_smem), "l"(tmap), "r"(mbar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
 // one lane of a fully converged warp; keeps the guarded region in the uniform datapath (descriptors in UR registers)
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;

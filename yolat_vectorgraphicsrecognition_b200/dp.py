@@ -76,9 +76,12 @@ class OverlappedGradSync(object):
       are captured into the step graph -- reduces the remaining head of the buffer, joins both collectives and scales
       by 1 / world.  Only that second, small all-reduce is exposed.
 
-    `overlap=False` drops the hooks: one collective over the whole buffer in `finish()` -- the variant to capture in a
-    CUDA graph (asynchronous NCCL work issued from autograd hooks inside a capture hung on torch 2.11 / NCCL 2.28;
-    tools/nccl_capture_probe.py lists what captures cleanly).
+    `side_stream=True` is the capturable form of the same overlap: the hook forks a side stream off the backward's
+    stream, issues the early all-reduce there synchronously (no Work handle outlives the hook) and `finish()` joins the
+    side stream back -- inside a CUDA-graph capture this becomes a parallel branch of the step graph.  (Asynchronous NCCL
+    work issued from autograd hooks inside a capture fails with cudaErrorStreamCaptureIsolation or hangs on torch 2.11 /
+    NCCL 2.28; tools/nccl_capture_probe.py and tools/nccl_hang_probe.py list what captures cleanly.)
+    `overlap=False` drops the hooks: one collective over the whole buffer in `finish()`.
 
     BatchNorm statistics stay rank-local (DDP-default semantics).  Gradients must be re-created every step
     (`zero_grad(set_to_none=True)`, what GraphedStep does): an existing `p.grad` makes autograd accumulate in place
@@ -86,9 +89,11 @@ class OverlappedGradSync(object):
     back to the copy-then-reduce schedule of `FlatGradients`.
     """
 
-    def __init__(self, model, group=None, early_prefixes=('prediction_cls',), overlap=True, async_early=True):
+    def __init__(self, model, group=None, early_prefixes=('prediction_cls',), overlap=True, async_early=True,
+                 side_stream=False):
         from . import ops
-        self.overlap, self.async_early = bool(overlap), bool(async_early)
+        self.overlap, self.async_early, self.side_stream = bool(overlap), bool(async_early), bool(side_stream)
+        self._side, self._side_pending = None, False
         named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
         self.params = [p for _, p in named]
         self.group = group
@@ -145,12 +150,22 @@ class OverlappedGradSync(object):
             self._work.wait()
             self._work = None
         if self.world() > 1 and self.split < self.numel:
-            self._work = dist.all_reduce(self.flat.narrow(0, self.split, self.numel - self.split),
-                                         op=dist.ReduceOp.SUM, group=self.group, async_op=self.async_early)
+            early = self.flat.narrow(0, self.split, self.numel - self.split)
+            if self.side_stream:
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.flat.device)
+                self._side.wait_stream(torch.cuda.current_stream(self.flat.device))     # fork: the early grads are final
+                with torch.cuda.stream(self._side):
+                    dist.all_reduce(early, op=dist.ReduceOp.SUM, group=self.group)
+                self._side_pending = True
+            else:
+                self._work = dist.all_reduce(early, op=dist.ReduceOp.SUM, group=self.group, async_op=self.async_early)
 
     def finish(self, _loss=None):
         """Join the early collective, reduce the rest, scale: p.grad = mean over ranks for every parameter."""
         self._count = 0
+        if not self.enabled:              # a step that must not communicate (see `enabled`)
+            return self.flat
         world = self.world()
         capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
         if not self.copy_mode and not (self._adopted(False) and self._adopted(True)):
@@ -161,6 +176,7 @@ class OverlappedGradSync(object):
             if self._work is not None:
                 self._work.wait()
                 self._work = None
+            self._join_side()
             src = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
             torch._foreach_copy_(self.views, src)
             if world > 1:
@@ -173,9 +189,15 @@ class OverlappedGradSync(object):
             if self._work is not None:
                 self._work.wait()
                 self._work = None
+        self._join_side()
         if world > 1:
             self.flat.mul_(1.0 / world)
         return self.flat
+
+    def _join_side(self):
+        if self._side_pending:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self._side)
+            self._side_pending = False
 
     def drain(self):
         """Join an early-bucket collective whose finish() was never called (the eager warm-up steps of a GraphedStep
@@ -185,6 +207,7 @@ class OverlappedGradSync(object):
         if self._work is not None:
             self._work.wait()
             self._work = None
+        self._join_side()
 
     def close(self):
         from . import ops

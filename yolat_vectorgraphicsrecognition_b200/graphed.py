@@ -143,6 +143,18 @@ class GraphedStep(object):
             entry.fresh = True
         return entry
 
+    def release(self):
+        """Drop every captured graph (and its static inputs).  Call it before `dist.destroy_process_group()` when `extra`
+        issued collectives: a captured NCCL kernel keeps the communicator referenced until its graph is destroyed."""
+        torch.cuda.synchronize(self.device)
+        self._staged.clear()
+        for entry in self._graphs.values():
+            entry.graph = None
+        self._graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize(self.device)
+
     def prefetch(self, batch):
         """Stage `batch` (host tensors, ideally a pinned PackedBatch) for the NEXT call on a copy stream, into the
         input set the step in flight is not using: its host->device copy overlaps the current step's kernels."""
