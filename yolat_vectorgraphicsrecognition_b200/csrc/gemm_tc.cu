@@ -47,6 +47,8 @@ struct Params {
   float* stat_part;      // [gridDim.y][2][N] column sum / sumsq of the stored tile (null = off)
   int a_vec, b_vec;      // 16-byte vector loads are legal for A / B
   int c_vec;             // 16-byte vector stores are legal for C
+  int tma_store;         // TMA variant: C leaves through cp.async.bulk.tensor stores (maps.c) instead of per-thread STG
+  int dbg;               // YOLAT_TC_DBG (timing experiments only): 1 = no hi/lo conversion, 2 = no C stores, 4 = no MMA
 };
 
 // ---- operand loaders -------------------------------------------------------------------------------
@@ -449,11 +451,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const Params p) {
 // where it was, lo into the neighbouring buffer -- elementwise, so the swizzle never has to be undone) and hand the
 // stage to the MMA warp.  No global load passes through registers; the loads of NST k-blocks are in flight per CTA.
 constexpr int WS_PRODUCERS = 8, WS_THREADS = (WS_PRODUCERS + 1 + 4) * 32, WS_THREADS_TMA = WS_THREADS + 32;
-struct alignas(64) TmaMaps { CUtensorMap a, b; };
+struct alignas(64) TmaMaps { CUtensorMap a, b, c; };
 template <int BN> struct WsCfg {
   static constexpr int NST = (BN == 128) ? 3 : 4;
   static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * BN * 128;
-  static constexpr uint32_t XPOSE_BYTES = 4 * 32 * 33 * 4;
+  // epilogue scratch per warp: a 32 x 33 transpose tile for the column statistics, or (TMA stores) two 32 x 32 fp32
+  // boxes in the SWIZZLE_128B layout of the output tensor map
+  static constexpr uint32_t XPOSE_BYTES = 4 * 2 * 4096;
   static constexpr size_t SMEM = (size_t)NST * STAGE_BYTES + XPOSE_BYTES + 1024;
 };
 
@@ -527,6 +531,7 @@ k_tc_gemm_ws(const Params p, const int gn, const int gm, const int ksplit, const
     while (s.tile < total) {
       mbar_wait(smem_u32(&bar_tma[st]), use & 1u);            // the raw fp32 k-block of A and B has landed
       uint8_t* sp = tiles + (uint32_t)st * STAGE_BYTES;
+      if (!(p.dbg & 1)) {
 #pragma unroll
       for (int i = 0; i < (int)(A_BYTES / 16) / (WS_PRODUCERS * 32); ++i) {
         const uint32_t off = (uint32_t)(tid + i * WS_PRODUCERS * 32) * 16u;
@@ -538,6 +543,7 @@ k_tc_gemm_ws(const Params p, const int gn, const int gm, const int ksplit, const
         store_split_fast(sp + 2 * A_BYTES, sp + 2 * A_BYTES + B_BYTES, off,
                          *reinterpret_cast<const float4*>(sp + 2 * A_BYTES + off));
       }
+      }
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&bar_full[st]));
       if (++st == NST) { st = 0; ++use; }
@@ -545,7 +551,7 @@ k_tc_gemm_ws(const Params p, const int gn, const int gm, const int ksplit, const
     }
   } else if (TMA && warp == WS_PRODUCERS + 5) {
     // =========================== TMA issue (TMA variant) =================================================
-    if (lane == 0) { tma_prefetch_desc(&maps.a); tma_prefetch_desc(&maps.b); }
+    if (lane == 0) { tma_prefetch_desc(&maps.a); tma_prefetch_desc(&maps.b); if (p.tma_store) tma_prefetch_desc(&maps.c); }
     Cur f;
     load_tile(blockIdx.x, f);
     int st = 0;
@@ -652,6 +658,7 @@ k_tc_gemm_ws(const Params p, const int gn, const int gm, const int ksplit, const
                                        : make_desc(sb + b_off, 16, 1024, LAYOUT_SW128);
             const uint64_t b_lo = B_MN ? make_desc(sb + B_BYTES + b_off, B_LBO, B_SBO, LAYOUT_SW128_BASE32B)
                                        : make_desc(sb + B_BYTES + b_off, 16, 1024, LAYOUT_SW128);
+            if (p.dbg & 4) continue;
             umma_tf32(d, a_lo, b_hi, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
             umma_tf32(d, a_hi, b_lo, IDESC, 1u);
             umma_tf32(d, a_hi, b_hi, IDESC, 1u);
@@ -666,7 +673,10 @@ k_tc_gemm_ws(const Params p, const int gn, const int gm, const int ksplit, const
   } else if (warp <= WS_PRODUCERS + 4) {
     // =========================== epilogue ================================================================
     const int q4 = warp & 3;                       // TMEM lane quarter this warp may read
-    float* xp = xpose + (warp - WS_PRODUCERS - 1) * (32 * 33);
+    float* xp = xpose + (warp - WS_PRODUCERS - 1) * 2048;
+    const uint32_t xp_u32 = tiles_u32 + NST * STAGE_BYTES + (uint32_t)(warp - WS_PRODUCERS - 1) * 8192u;
+    const bool tstore = TMA && p.tma_store;
+    uint32_t nbox = 0;                              // boxes this warp has handed to the TMA store engine
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       Cur c;
@@ -713,6 +723,41 @@ k_tc_gemm_ws(const Params p, const int gn, const int gm, const int ksplit, const
             for (int i = 0; i < 32; ++i) if (i < cols) v[i] += __ldg(p.bias + col0 + i);
           }
         }
+        if (tstore) {
+          // registers -> swizzled 32 x 32 box (row = lane: 8 conflict-free 16-byte stores) -> one TMA store per box; the
+          // store engine clips rows >= M and columns >= N.  Two boxes per warp alternate, so the store of box j drains
+          // while box j + 1 is filled.
+          uint8_t* box = reinterpret_cast<uint8_t*>(xp) + (nbox & 1u) * 4096u;
+          if (nbox >= 2) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(box + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (p.stat_part) {
+            float sm_ = 0.f, ss_ = 0.f;
+            for (int r = 0; r < rows_w; ++r) {
+              const float z = *reinterpret_cast<const float*>(box + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+              sm_ += z;
+              ss_ = fmaf(z, z, ss_);
+            }
+            if (lane < cols) {
+              const int64_t pi = (int64_t)(c.m0 / BM) * 4 + q4;
+              p.stat_part[(pi * 2 + 0) * p.N + col0 + lane] = sm_;
+              p.stat_part[(pi * 2 + 1) * p.N + col0 + lane] = ss_;
+            }
+          }
+          if (lane == 0 && rows_w > 0 && !(p.dbg & 2)) {
+            tma_store_2d(&maps.c, xp_u32 + (nbox & 1u) * 4096u, col0, c.m0 + q4 * 32);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++nbox;
+          continue;
+        }
         if (p.stat_part) {      // column statistics of z = acc + bias (before any accumulate: stats GEMMs never accumulate)
 #pragma unroll
           for (int i = 0; i < 32; ++i) xp[lane * 33 + i] = v[i];
@@ -730,7 +775,7 @@ k_tc_gemm_ws(const Params p, const int gn, const int gm, const int ksplit, const
           }
           __syncwarp();
         }
-        if (row_ok) {
+        if (row_ok && !(p.dbg & 2)) {
           float* o = p.C + (int64_t)row * p.ldc + col0;
           if (p.c_vec && cols == 32) {
 #pragma unroll
@@ -750,6 +795,7 @@ k_tc_gemm_ws(const Params p, const int gn, const int gm, const int ksplit, const
         }
       }
     }
+    if (tstore && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every box has reached memory
   }
   tc_fence_before();
   __syncthreads();
@@ -829,7 +875,13 @@ static cudaError_t launch_ws(const Params& p, int gn, int gm, int ksplit, cudaSt
   if (tma_mode_enabled(MODE) && p.a_vec && p.b_vec && !p.a_sc && !p.b_sc && p.K < (1ll << 31)) {
     const bool ok_a = a_k ? encode_map(&maps.a, p.A, p.lda, p.K, p.M, BM, false) : encode_map(&maps.a, p.A, p.lda, p.M, p.K, 32, true);
     const bool ok_b = b_k ? encode_map(&maps.b, p.B, p.ldb, p.K, p.N, BN, false) : encode_map(&maps.b, p.B, p.ldb, p.N, p.K, 32, true);
-    if (ok_a && ok_b) return launch_ws2<MODE, BN, true, true>(p, gn, gm, ksplit, maps, st);
+    if (ok_a && ok_b) {
+      Params q = p;
+      static const bool store_on = !(getenv("YOLAT_TC_TMA_STORE") && getenv("YOLAT_TC_TMA_STORE")[0] == '0');
+      // C through TMA stores: whole-K tiles written once (no split-K partials, no read-modify-write)
+      q.tma_store = store_on && ksplit == 1 && !p.accumulate && p.c_vec && encode_map(&maps.c, p.C, p.ldc, p.N, p.M, 32, false);
+      return launch_ws2<MODE, BN, true, true>(q, gn, gm, ksplit, maps, st);
+    }
   }
   const bool fast = p.a_vec && p.b_vec && ((a_k ? p.K : (int64_t)p.M) % 4 == 0) && ((b_k ? p.K : (int64_t)p.N) % 4 == 0);
   return fast ? launch_ws2<MODE, BN, true, false>(p, gn, gm, ksplit, maps, st)
@@ -896,6 +948,26 @@ static TcPlan tc_plan(int M, int N, int64_t K, GemmMode mode, bool want_stats) {
 
 static int gemm_tc(const GemmArgs& a, GemmMode mode, Arena& ws, float* stat_part, int* stat_nparts, cudaStream_t st) {
   const TcPlan pl = tc_plan(a.M, a.N, a.K, mode, stat_nparts != nullptr);
+  // Wave quantisation: one CTA per SM walks the tile list, so 157 row tiles cost two full passes for 1.06 passes of work
+  // (dx = dz W of the fusion block: M = 20000, N = 128).  When a short tail spills over the last full wave, the rows of
+  // the full waves run as one call and the tail rows as a second, much smaller problem that the planner splits along K.
+  // Row-disjoint outputs: bias / accumulate keep their meaning; not for dW (rows are the reduction) nor when the
+  // epilogue has to deliver column statistics of the whole matrix.
+  static const bool tail_split = !(getenv("YOLAT_TC_TAIL") && getenv("YOLAT_TC_TAIL")[0] == '0');
+  if (tail_split && mode != GEMM_TN && !stat_nparts && pl.ksplit == 1 && a.K >= 8 * tc::BK) {
+    const int64_t tiles = (int64_t)pl.gm * pl.gn;
+    const int64_t full = tiles / kNumSMs * kNumSMs;
+    const int gm_main = (int)(full / pl.gn);
+    if (full > 0 && tiles - full > 0 && (tiles - full) * 4 <= kNumSMs && gm_main > 0 && gm_main < pl.gm) {
+      GemmArgs head = a, tail = a;
+      head.M = gm_main * tc::BM;
+      tail.M = a.M - head.M;
+      tail.A = a.A ? a.A + (int64_t)head.M * a.lda : nullptr;
+      tail.C = a.C ? a.C + (int64_t)head.M * a.ldc : nullptr;
+      YOLAT_TRY(gemm_tc(head, mode, ws, nullptr, nullptr, st));
+      return gemm_tc(tail, mode, ws, nullptr, nullptr, st);
+    }
+  }
   float* part = nullptr;
   if (pl.ksplit > 1) part = ws.take((int64_t)pl.ksplit * a.M * a.N);
   if (stat_nparts) *stat_nparts = pl.ksplit > 1 ? 0 : pl.gm * 4;    // one partial per epilogue warp (32 rows)
@@ -912,6 +984,8 @@ static int gemm_tc(const GemmArgs& a, GemmMode mode, Arena& ws, float* stat_part
   p.a_vec = aligned16p(a.A) && (a.lda % 4 == 0);
   p.b_vec = aligned16p(a.B) && (a.ldb % 4 == 0);
   p.c_vec = aligned16p(a.C) && (a.ldc % 4 == 0);
+  static const int dbg = getenv("YOLAT_TC_DBG") ? atoi(getenv("YOLAT_TC_DBG")) : 0;
+  p.dbg = dbg;
   dim3 grid(pl.gn, pl.gm, pl.ksplit);
   cudaError_t e = cudaSuccess;
   ProfScope prof(YOLAT_PROF_GEMM, st);

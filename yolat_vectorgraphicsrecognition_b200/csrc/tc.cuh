@@ -93,6 +93,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
                ::"r"(dst_smem), "l"(tmap), "r"(mbar), "r"(c0), "r"(c1)
                : "memory");
 }
+// shared -> global: one box of the tensor map, clipped to the tensor's extents; completion through bulk async-groups
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src_smem, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
