@@ -94,6 +94,7 @@ class OverlappedGradSync(object):
         from . import ops
         self.overlap, self.async_early, self.side_stream = bool(overlap), bool(async_early), bool(side_stream)
         self._side, self._side_pending = None, False
+        self._avg = None
         named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
         self.params = [p for _, p in named]
         self.group = group
@@ -127,6 +128,12 @@ class OverlappedGradSync(object):
     def world(self):
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
 
+    def _op(self):
+        """ncclAvg folds the 1 / world scaling into the collective (no separate kernel over the buffer); gloo has no AVG."""
+        if self._avg is None:
+            self._avg = dist.is_initialized() and dist.get_backend(self.group) == 'nccl'
+        return dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+
     def _adopted(self, early):
         n_late = len(self.late_params)
         params, views = (self.early_params, self.views[n_late:]) if early else (self.late_params, self.views[:n_late])
@@ -156,10 +163,10 @@ class OverlappedGradSync(object):
                     self._side = torch.cuda.Stream(device=self.flat.device)
                 self._side.wait_stream(torch.cuda.current_stream(self.flat.device))     # fork: the early grads are final
                 with torch.cuda.stream(self._side):
-                    dist.all_reduce(early, op=dist.ReduceOp.SUM, group=self.group)
+                    dist.all_reduce(early, op=self._op(), group=self.group)
                 self._side_pending = True
             else:
-                self._work = dist.all_reduce(early, op=dist.ReduceOp.SUM, group=self.group, async_op=self.async_early)
+                self._work = dist.all_reduce(early, op=self._op(), group=self.group, async_op=self.async_early)
 
     def finish(self, _loss=None):
         """Join the early collective, reduce the rest, scale: p.grad = mean over ranks for every parameter."""
@@ -167,6 +174,7 @@ class OverlappedGradSync(object):
         if not self.enabled:              # a step that must not communicate (see `enabled`)
             return self.flat
         world = self.world()
+        self._op()
         capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
         if not self.copy_mode and not (self._adopted(False) and self._adopted(True)):
             if capturing:
@@ -180,17 +188,17 @@ class OverlappedGradSync(object):
             src = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
             torch._foreach_copy_(self.views, src)
             if world > 1:
-                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(self.flat, op=self._op(), group=self.group)
             for p, v in zip(self.params, self.views):
                 p.grad = v
         elif world > 1:
             if self.split > 0:
-                dist.all_reduce(self.flat.narrow(0, 0, self.split), op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(self.flat.narrow(0, 0, self.split), op=self._op(), group=self.group)
             if self._work is not None:
                 self._work.wait()
                 self._work = None
         self._join_side()
-        if world > 1:
+        if world > 1 and not self._avg:
             self.flat.mul_(1.0 / world)
         return self.flat
 
