@@ -73,3 +73,48 @@ def test_gemm_large_magnitude_spread():
     b = torch.randn(64, 96, generator=g) * torch.logspace(6, -6, 96)
     ref = a.double() @ b.double().t()
     assert max_rel(ops.gemm(0, a.cuda(), b.cuda()), ref) < TOL
+
+
+def test_gemm_tma_edges():
+    """The TMA-fed path at its edges: rows spilling over the last full wave of 148 tiles (tail split along K), outputs
+    narrower than one 32-column store box, reductions that are not a multiple of the 32-wide k-block, column-slice
+    operands (row pitch != row length) and an output slice (TMA stores must clip to the slice)."""
+    from yolat_vectorgraphicsrecognition_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    for mode, M, N, K in ((1, 20000, 128, 1024), (0, 19000, 128, 320), (0, 4100, 100, 72), (1, 777, 36, 200),
+                          (2, 96, 40, 7001), (0, 300, 20, 44)):
+        a, b = _operands(mode, M, N, K, g)
+        assert max_rel(ops.gemm(mode, a.cuda(), b.cuda()), _ref(mode, a, b)) < TOL, (mode, M, N, K)
+    wide_a = torch.randn(3000, 256, generator=g).cuda()
+    w = torch.randn(96, 128, generator=g).cuda()
+    wide_c = torch.zeros(3000, 320).cuda()
+    a = wide_a[:, 64:192]
+    ops.gemm(0, a, w, out=wide_c[:, 128:224])
+    assert max_rel(wide_c[:, 128:224], a.double().cpu() @ w.double().cpu().t()) < TOL
+    assert float(wide_c[:, :128].abs().max()) == 0.0 and float(wide_c[:, 224:].abs().max()) == 0.0
+
+
+_TMA_ENV_SCRIPT = r'''
+import sys, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+import test_gpu_gemm as t
+for shape in t.SHAPES:
+    t.test_gemm_matches_fp64(*shape)
+t.test_gemm_strided_views(); t.test_gemm_large_magnitude_spread(); t.test_gemm_tma_edges()
+print('RESULT ok')
+'''
+
+
+@pytest.mark.parametrize('env', [{'YOLAT_TC_TMA': '0'}, {'YOLAT_TC_TMA_STORE': '0'}, {'YOLAT_TC_TAIL': '0'}])
+def test_gemm_register_loader_paths_keep_parity(env):
+    """The GEMM variants behind the switches (register loaders instead of TMA loads, per-thread stores instead of TMA
+    stores, no tail split) must pass the same shapes."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    p = subprocess.run([sys.executable, '-c', _TMA_ENV_SCRIPT % dict(root=root, tests=os.path.join(root, 'tests'))], env=e,
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and 'RESULT ok' in p.stdout, (env, p.stderr[-2000:])

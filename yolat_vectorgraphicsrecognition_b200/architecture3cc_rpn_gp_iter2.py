@@ -38,6 +38,17 @@ def _dev(t, device):
     return t if t.is_cuda else t.to(device, non_blocking=True)
 
 
+_AUX_STREAMS = {}
+
+
+def _aux_stream(dev):
+    """One library-owned side stream per device (module state, not model state: models stay deep-copyable)."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _AUX_STREAMS:
+        _AUX_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _AUX_STREAMS[key]
+
+
 class Backbone(torch.nn.Module):
     """:15-71"""
 
@@ -96,6 +107,7 @@ class Backbone(torch.nn.Module):
         """Fused variant used by SparseCADGCN.forward: returns scatter(out_feat, 'max') [B, 1024 + fusion_dims]
         (:62-63 + :122 in one op) and out_feat_super."""
         feats, feats_super = self._trunk(x, edges, edge_weights, edge_attrs)
+        seg.join()                      # built on a side stream while the GraphConv stack ran (SparseCADGCN.forward)
         stages = self.fusion_block.stages()
         if len(stages) == 1 and stages[0][0] == 'stage' and stages[0][2] is not None and stages[0][3]:
             _, lin, bn, _ = stages[0]
@@ -160,7 +172,8 @@ class SparseCADGCN(torch.nn.Module):
         # gather, KeyError in build_data); the graph build counts them on the device, and the count is read back -- one
         # host sync -- wherever a sync exists anyway (predict) or when `check_graph` is set (YOLAT_CHECK_GRAPH=1).
         graph = CSRGraph(edge.T, x.shape[0], check=self.check_graph or self._in_predict)
-        seg = Segments(bbox_idx, pred_bbox.shape[0])           # one proposal per bbox row: no index.max() sync
+        # one proposal per bbox row: no index.max() sync; built beside the GraphConv stack, joined in forward_pooled
+        seg = Segments(bbox_idx, pred_bbox.shape[0], side_stream=_aux_stream(dev))
         pooled, out_feat_cls_super = self.cls_net.forward_pooled(x, [graph], [None], [e_attr], seg)   # :121-122
         out_feat_cls = torch.cat([pooled, out_feat_cls_super], dim=1)                                  # :127
         pred_cls = self.prediction_cls(out_feat_cls)                                                   # :128

@@ -652,17 +652,23 @@ __global__ void __launch_bounds__(L<TILE>::THREADS, TILE == 64 ? 2 : 1) k_edge_b
   if (warp == 0) tmem_dealloc(tmem_d, 256);
 }
 
-// slot-ordered records of one pass: (dst, src, eid, 0) | attribute row; by_source walks the CSR-by-source order
+// slot-ordered records of the passes: (dst, src, eid, 0) | attribute row, once in CSR-by-target order (D1, D2T) and once
+// in CSR-by-source order (D2S).  One launch builds both: the two dependent-load chains of a thread overlap.
 __global__ void k_edge_bwd_records(const int32_t* __restrict__ src_t, const int32_t* __restrict__ dst_t,
                                    const int32_t* __restrict__ eid_t, const int32_t* __restrict__ slot_s,
-                                   const float4* __restrict__ attr, int64_t E, int4* __restrict__ rec_idx,
-                                   float4* __restrict__ rec_attr) {
+                                   const float4* __restrict__ attr, int64_t E, int4* __restrict__ rec_idx_t,
+                                   float4* __restrict__ rec_attr_t, int4* __restrict__ rec_idx_s,
+                                   float4* __restrict__ rec_attr_s) {
   const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k >= E) return;
-  const int64_t s = slot_s ? (int64_t)__ldg(slot_s + k) : k;
-  const int e = __ldg(eid_t + s);
-  rec_idx[k] = make_int4(__ldg(dst_t + s), __ldg(src_t + s), e, 0);
-  rec_attr[k] = __ldg(attr + e);
+  const int64_t s = (int64_t)__ldg(slot_s + k);
+  const int et = __ldg(eid_t + k), es = __ldg(eid_t + s);
+  const int4 it = make_int4(__ldg(dst_t + k), __ldg(src_t + k), et, 0), is = make_int4(__ldg(dst_t + s), __ldg(src_t + s), es, 0);
+  const float4 at = __ldg(attr + et), as = __ldg(attr + es);
+  rec_idx_t[k] = it;
+  rec_attr_t[k] = at;
+  rec_idx_s[k] = is;
+  rec_attr_s[k] = as;
 }
 
 // Node-level tail of the backward (see the header): dW2, dW1c and dP | dQ from the per-CTA partials and row sums.
@@ -798,9 +804,8 @@ int edge_bwd_fused(const GraphView& g, int64_t N, int64_t E, const float* pq, in
   int4* ri_s = reinterpret_cast<int4*>(w.rec_s);
   float4* ra_s = reinterpret_cast<float4*>(w.rec_s + 4 * E);
   const unsigned nb = (unsigned)cdiv(E, 256);
-  k_edge_bwd_records<<<nb, 256, 0, st>>>(g.src_t, g.dst_t, g.eid_t, nullptr, reinterpret_cast<const float4*>(attr), E, ri_t, ra_t);
-  YOLAT_CHECK_LAUNCH();
-  k_edge_bwd_records<<<nb, 256, 0, st>>>(g.src_t, g.dst_t, g.eid_t, g.slot_s, reinterpret_cast<const float4*>(attr), E, ri_s, ra_s);
+  k_edge_bwd_records<<<nb, 256, 0, st>>>(g.src_t, g.dst_t, g.eid_t, g.slot_s, reinterpret_cast<const float4*>(attr), E, ri_t, ra_t,
+                                         ri_s, ra_s);
   YOLAT_CHECK_LAUNCH();
 
   Params p{};

@@ -36,6 +36,7 @@ __global__ void k_count_index(const int64_t* __restrict__ index, int64_t M, int6
 // ---- exclusive scan, one CTA per array (blockIdx.x selects the array) ------------------------------
 // cnt arrives in out[0..n) (counts were accumulated in place), result: out[0..n] exclusive prefix.
 // Optionally writes deg_inv = 1/max(cnt,1).
+template <int IPT>
 __global__ void __launch_bounds__(1024) k_scan_inplace(int32_t* a0, int32_t* a1, int64_t n, float* deg_inv0) {
   int32_t* a = blockIdx.x == 0 ? a0 : a1;
   float* deg_inv = blockIdx.x == 0 ? deg_inv0 : nullptr;
@@ -45,49 +46,69 @@ __global__ void __launch_bounds__(1024) k_scan_inplace(int32_t* a0, int32_t* a1,
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) carry = 0;
   __syncthreads();
-  // tiles of 1024*4 elements; each thread owns 4 consecutive elements
-  for (int64_t base = 0; base < n; base += 4096) {
-    int64_t i0 = base + tid * 4;
-    int32_t v[4];
+  // Tiles of 1024 * IPT elements.  Warp w owns the contiguous range [w * 32 * IPT, (w + 1) * 32 * IPT) of the tile and
+  // walks it in IPT coalesced rows of 32 (all loads issued up front); IPT is chosen so that the graphs of the timed
+  // configurations (N <= 32768) are ONE tile: one round of loads, two barriers.
+  for (int64_t base = 0; base < n; base += 1024 * IPT) {
+    const int64_t w0 = base + (int64_t)wid * (32 * IPT);
+    int32_t v[IPT];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = (i0 + q < n) ? a[i0 + q] : 0;
+    for (int q = 0; q < IPT; ++q) {
+      const int64_t i = w0 + q * 32 + lane;
+      v[q] = i < n ? a[i] : 0;
+    }
     if (deg_inv) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (i0 + q < n) deg_inv[i0 + q] = 1.0f / (float)max(v[q], 1);
+      for (int q = 0; q < IPT; ++q) {
+        const int64_t i = w0 + q * 32 + lane;
+        if (i < n) deg_inv[i] = 1.0f / (float)max(v[q], 1);
+      }
     }
-    const int32_t tsum = v[0] + v[1] + v[2] + v[3];
-    int32_t inc = tsum;
+    // inclusive scan of every row of 32, rows chained through a running total
+    int32_t inc[IPT];
+    int32_t run = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
+    for (int q = 0; q < IPT; ++q) {
+      int32_t x = v[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t t = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += t;
+      }
+      inc[q] = run + x;
+      run += __shfl_sync(0xffffffffu, x, 31);
     }
-    if (lane == 31) warp_off[wid] = inc;
+    if (lane == 0) warp_off[wid] = run;             // this warp's total
     __syncthreads();
     if (wid == 0) {
       const int32_t w = warp_off[lane];
       int32_t winc = w;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        int32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+        const int32_t t = __shfl_up_sync(0xffffffffu, winc, o);
         if (lane >= o) winc += t;
       }
       warp_off[lane] = winc - w;  // exclusive offset of each warp inside the tile
       if (lane == 31) tile_total = winc;
     }
     __syncthreads();
-    int32_t excl = carry + warp_off[wid] + (inc - tsum);
+    const int32_t off = carry + warp_off[wid];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (i0 + q < n) a[i0 + q] = excl;
-      excl += v[q];
+    for (int q = 0; q < IPT; ++q) {
+      const int64_t i = w0 + q * 32 + lane;
+      if (i < n) a[i] = off + inc[q] - v[q];
     }
     __syncthreads();
     if (tid == 0) carry += tile_total;
     __syncthreads();
   }
   if (tid == 0) a[n] = carry;
+}
+static void launch_scan(int arrays, int32_t* a0, int32_t* a1, int64_t n, float* deg_inv0, cudaStream_t st) {
+  if (n <= 1024 * 4) k_scan_inplace<4><<<arrays, 1024, 0, st>>>(a0, a1, n, deg_inv0);
+  else if (n <= 1024 * 8) k_scan_inplace<8><<<arrays, 1024, 0, st>>>(a0, a1, n, deg_inv0);
+  else if (n <= 1024 * 16) k_scan_inplace<16><<<arrays, 1024, 0, st>>>(a0, a1, n, deg_inv0);
+  else k_scan_inplace<32><<<arrays, 1024, 0, st>>>(a0, a1, n, deg_inv0);
 }
 
 // ---- fill + per-row sort -------------------------------------------------------------------------
@@ -102,7 +123,26 @@ __global__ void k_fill_target(const int64_t* __restrict__ edge, int64_t se, int6
   eid_t[pos] = (int32_t)e;
 }
 
+// Rows are short (Bezier-curve graphs: 4 neighbours, proposals: ~16 nodes): up to 8 values are sorted in registers with
+// one round of loads and one of stores; longer rows fall back to the in-memory insertion sort.
 __device__ __forceinline__ void insertion_sort(int32_t* a, int n) {
+  if (n <= 1) return;
+  if (n <= 8) {
+    int32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = i < n ? a[i] : 0x7fffffff;
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {          // odd-even transposition network, fully unrolled
+#pragma unroll
+      for (int i = pass & 1; i + 1 < 8; i += 2) {
+        const int32_t lo = min(r[i], r[i + 1]), hi = max(r[i], r[i + 1]);
+        r[i] = lo; r[i + 1] = hi;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i < n) a[i] = r[i];
+    return;
+  }
   for (int i = 1; i < n; ++i) {
     int32_t key = a[i];
     int j = i - 1;
@@ -209,19 +249,19 @@ int yolat_graph_build(const int64_t* edge, int64_t se, int64_t sc, int64_t E, in
     k_count_edges<<<(unsigned)cdiv(E, T), T, 0, st>>>(edge, se, sc, E, N, rowptr_t, rowptr_s, const_cast<int32_t*>(v.err));
     YOLAT_CHECK_LAUNCH();
   }
-  k_scan_inplace<<<2, 1024, 0, st>>>(rowptr_t, rowptr_s, N, const_cast<float*>(v.deg_inv));
+  launch_scan(2, rowptr_t, rowptr_s, N, const_cast<float*>(v.deg_inv), st);
   YOLAT_CHECK_LAUNCH();
   if (E > 0 && N > 0) {
     k_fill_target<<<(unsigned)cdiv(E, T), T, 0, st>>>(edge, se, sc, E, N, rowptr_t, v.cursor_t, const_cast<int32_t*>(v.eid_t));
     YOLAT_CHECK_LAUNCH();
-    k_sort_target_rows<<<(unsigned)cdiv(N, T), T, 0, st>>>(edge, se, N, rowptr_t, const_cast<int32_t*>(v.eid_t),
+    k_sort_target_rows<<<(unsigned)cdiv(N, 64), 64, 0, st>>>(edge, se, N, rowptr_t, const_cast<int32_t*>(v.eid_t),
                                                            const_cast<int32_t*>(v.src_t), const_cast<int32_t*>(v.dst_t),
                                                            v.slot_of_edge);
     YOLAT_CHECK_LAUNCH();
     k_fill_source<<<(unsigned)cdiv(E, T), T, 0, st>>>(edge, se, sc, E, N, rowptr_s, v.cursor_s, v.slot_of_edge,
                                                       const_cast<int32_t*>(v.slot_s));
     YOLAT_CHECK_LAUNCH();
-    k_sort_rows<<<(unsigned)cdiv(N, T), T, 0, st>>>(N, rowptr_s, const_cast<int32_t*>(v.slot_s));
+    k_sort_rows<<<(unsigned)cdiv(N, 64), 64, 0, st>>>(N, rowptr_s, const_cast<int32_t*>(v.slot_s));
     YOLAT_CHECK_LAUNCH();
   }
   return YOLAT_OK;
@@ -242,13 +282,13 @@ int yolat_segments_build(const int64_t* index, int64_t M, int64_t S, int32_t* se
     k_count_index<<<(unsigned)cdiv(M, T), T, 0, st>>>(index, M, S, segptr);
     YOLAT_CHECK_LAUNCH();
   }
-  k_scan_inplace<<<1, 1024, 0, st>>>(segptr, segptr, S, nullptr);
+  launch_scan(1, segptr, segptr, S, nullptr, st);
   YOLAT_CHECK_LAUNCH();
   if (M > 0 && S > 0) {
     k_fill_index<<<(unsigned)cdiv(M, T), T, 0, st>>>(index, M, S, segptr, v.cursor, const_cast<int32_t*>(v.perm),
                                                      const_cast<int32_t*>(v.seg_of_row));
     YOLAT_CHECK_LAUNCH();
-    k_sort_rows<<<(unsigned)cdiv(S, T), T, 0, st>>>(S, segptr, const_cast<int32_t*>(v.perm));
+    k_sort_rows<<<(unsigned)cdiv(S, 64), 64, 0, st>>>(S, segptr, const_cast<int32_t*>(v.perm));
     YOLAT_CHECK_LAUNCH();
   }
   return YOLAT_OK;

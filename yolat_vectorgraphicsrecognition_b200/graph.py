@@ -58,7 +58,10 @@ class CSRGraph(object):
 class Segments(object):
     """Rows grouped by an index vector (proposals from `bbox_idx`); `num_segments` = scatter's dim_size."""
 
-    def __init__(self, index, num_segments=None):
+    def __init__(self, index, num_segments=None, side_stream=None):
+        """`side_stream`: build on that stream, forked off the current one (stream-ordered, capturable); the caller must
+        `join()` before the first use -- the proposal index is only needed after the GraphConv stack, so its four small
+        kernels leave the critical path."""
         L.require_cuda(index)
         if index.dtype != torch.int64:
             index = index.long()
@@ -72,8 +75,19 @@ class Segments(object):
         lib = L.lib()
         self.buf = torch.empty(max(int(lib.yolat_segments_ints(self.M, self.S)), 1), dtype=torch.int32,
                                device=self.device)
-        L.check(lib.yolat_segments_build(index.data_ptr(), self.M, self.S, self.buf.data_ptr(), L.stream()),
-                'segments_build')
+        self._side = side_stream
+        if side_stream is not None:
+            side_stream.wait_stream(torch.cuda.current_stream(self.device))
+            st = side_stream.cuda_stream
+        else:
+            st = L.stream()
+        L.check(lib.yolat_segments_build(index.data_ptr(), self.M, self.S, self.buf.data_ptr(), st), 'segments_build')
+
+    def join(self):
+        """The current stream continues after the build (no-op unless built on a side stream)."""
+        if self._side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._side = None
 
     def ptr(self):
         return self.buf.data_ptr()
