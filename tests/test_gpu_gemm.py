@@ -82,7 +82,7 @@ def test_gemm_tma_edges():
     from yolat_vectorgraphicsrecognition_b200 import ops
     g = torch.Generator().manual_seed(21)
     for mode, M, N, K in ((1, 20000, 128, 1024), (0, 19000, 128, 320), (0, 4100, 100, 72), (1, 777, 36, 200),
-                          (2, 96, 40, 7001), (0, 300, 20, 44)):
+                          (2, 96, 40, 7001), (0, 300, 20, 44), (2, 128, 5, 20000), (2, 200, 8, 777), (2, 64, 1, 130)):
         a, b = _operands(mode, M, N, K, g)
         assert max_rel(ops.gemm(mode, a.cuda(), b.cuda()), _ref(mode, a, b)) < TOL, (mode, M, N, K)
     wide_a = torch.randn(3000, 256, generator=g).cuda()
@@ -105,7 +105,8 @@ print('RESULT ok')
 '''
 
 
-@pytest.mark.parametrize('env', [{'YOLAT_TC_TMA': '0'}, {'YOLAT_TC_TMA_STORE': '0'}, {'YOLAT_TC_TAIL': '0'}])
+@pytest.mark.parametrize('env', [{'YOLAT_TC_TMA': '0'}, {'YOLAT_TC_TMA_STORE': '0'}, {'YOLAT_TC_TAIL': '0'},
+                                 {'YOLAT_TC_SKINNY': '0'}])
 def test_gemm_register_loader_paths_keep_parity(env):
     """The GEMM variants behind the switches (register loaders instead of TMA loads, per-thread stores instead of TMA
     stores, no tail split) must pass the same shapes."""

@@ -147,6 +147,17 @@ def f32c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def f32rows(t):
+    """fp32 matrix whose rows are contiguous (row pitch >= row length): column slices of a wider matrix -- what the
+    backward of `torch.cat(..., dim=1)` hands to the producers of its inputs -- pass through without a copy; the C-ABI
+    takes the pitch as `ld`."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        return t
+    return t if t.is_contiguous() else t.contiguous()
+
+
 class _Workspace(object):
     """One grow-only fp32 scratch buffer per device, shared by all calls on the same stream order.
 

@@ -65,9 +65,19 @@ __device__ __forceinline__ void reduce_parts2(const float* __restrict__ part, in
   }
   sm[0][ty][tx] = a; sm[1][ty][tx] = b;
   __syncthreads();
-  if (ty == 0) {
-#pragma unroll 4
-    for (int q = 1; q < 32; ++q) { a += sm[0][q][tx]; b += sm[1][q][tx]; }
+  if (ty == 0) {      // fixed order, four independent chains per sum (the loads pipeline instead of serialising)
+    double a1 = 0.0, a2 = 0.0, a3 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+    a = sm[0][0][tx]; b = sm[1][0][tx];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) { a += sm[0][q][tx]; b += sm[1][q][tx]; }
+#pragma unroll
+    for (int q = 8; q < 16; ++q) { a1 += sm[0][q][tx]; b1 += sm[1][q][tx]; }
+#pragma unroll
+    for (int q = 16; q < 24; ++q) { a2 += sm[0][q][tx]; b2 += sm[1][q][tx]; }
+#pragma unroll
+    for (int q = 24; q < 32; ++q) { a3 += sm[0][q][tx]; b3 += sm[1][q][tx]; }
+    a = (a + a1) + (a2 + a3);
+    b = (b + b1) + (b2 + b3);
   }
   s = a; t = b;
 }
@@ -77,9 +87,19 @@ __global__ void __launch_bounds__(1024) k_bn_finalize(const float* __restrict__ 
   const int c = blockIdx.x * 32 + threadIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && training && bn.num_batches_tracked)
     *bn.num_batches_tracked += 1;
+  // the affine parameters and running buffers do not depend on the reduction: request them first so that their latency
+  // hides behind the partial sums (this kernel is a chain of dependent round trips, not a bandwidth problem)
+  const bool fin = threadIdx.y == 0 && c < C;
+  float w = 0.f, b = 0.f, rm = 0.f, rv = 0.f;
+  if (fin) {
+    w = bn.w[c];
+    b = bn.b[c];
+    if (bn.running_mean) rm = bn.running_mean[c];
+    if (bn.running_var) rv = bn.running_var[c];
+  }
   double s = 0.0, ss = 0.0;
   if (training) reduce_parts2(part, nparts, C, c, s, ss);
-  if (threadIdx.y != 0 || c >= C) return;
+  if (!fin) return;
   float mean, var;
   if (training) {
     const double mu = s / (double)M;
@@ -87,19 +107,19 @@ __global__ void __launch_bounds__(1024) k_bn_finalize(const float* __restrict__ 
     if (v < 0.0) v = 0.0;
     mean = (float)mu;
     var = (float)v;
-    if (bn.running_mean) bn.running_mean[c] = (1.f - kBnMomentum) * bn.running_mean[c] + kBnMomentum * mean;
+    if (bn.running_mean) bn.running_mean[c] = (1.f - kBnMomentum) * rm + kBnMomentum * mean;
     if (bn.running_var) {
       const double unbiased = M > 1 ? v * (double)M / (double)(M - 1) : v;
-      bn.running_var[c] = (1.f - kBnMomentum) * bn.running_var[c] + kBnMomentum * (float)unbiased;
+      bn.running_var[c] = (1.f - kBnMomentum) * rv + kBnMomentum * (float)unbiased;
     }
   } else {
-    mean = bn.running_mean[c];
-    var = bn.running_var[c];
+    mean = rm;
+    var = rv;
   }
   const float invstd = 1.0f / sqrtf(var + kBnEps);
-  const float sc = bn.w[c] * invstd;
+  const float sc = w * invstd;
   stat[c] = sc;
-  stat[C + c] = bn.b[c] - mean * sc;
+  stat[C + c] = b - mean * sc;
   stat[2 * C + c] = mean;
   stat[3 * C + c] = invstd;
 }

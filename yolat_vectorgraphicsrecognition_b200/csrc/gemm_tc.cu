@@ -910,6 +910,61 @@ __global__ void k_splitk_sum_deep(const float* __restrict__ part, int ksplit, in
 
 static bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---- skinny dW ------------------------------------------------------------------------------------------------------
+// dW = dy^T x with a handful of input columns (the head GraphConv reads the 5 raw curve features): a 128 x 64 tensor-core
+// tile would be 92 % padding.  One thread per output row m keeps the N <= 8 accumulators of its row; a CTA walks
+// SK_ROWS reduction rows (dy row segment coalesced across the threads, the x row is a broadcast) and writes one partial
+// [M, N]; the partials are summed in fixed order by k_splitk_sum_deep.
+constexpr int SK_ROWS = 128, SK_MAXN = 8, SK_GROUPS = 4;
+__global__ void __launch_bounds__(64 * SK_GROUPS) k_tn_skinny(const float* __restrict__ A, int64_t lda,
+                                                              const float* __restrict__ B, int64_t ldb, int M, int N,
+                                                              int64_t K, float* __restrict__ part) {
+  const int mi = threadIdx.x & 63, grp = threadIdx.x >> 6;          // 64 output rows per CTA, SK_GROUPS row lanes
+  const int m = blockIdx.y * 64 + mi;
+  const int64_t k0 = (int64_t)blockIdx.x * SK_ROWS;
+  const int rows = (int)min((int64_t)SK_ROWS, K - k0);
+  __shared__ float xs[SK_ROWS * SK_MAXN];
+  __shared__ float red[SK_GROUPS][64][SK_MAXN + 1];
+  for (int i = threadIdx.x; i < SK_ROWS * SK_MAXN; i += 64 * SK_GROUPS) {
+    const int r = i / SK_MAXN, j = i % SK_MAXN;
+    xs[i] = (r < rows && j < N) ? B[(k0 + r) * ldb + j] : 0.f;
+  }
+  __syncthreads();
+  float acc[SK_MAXN];
+#pragma unroll
+  for (int j = 0; j < SK_MAXN; ++j) acc[j] = 0.f;
+  const int mc = m < M ? m : M - 1;
+#pragma unroll 1
+  for (int i0 = 0; i0 < SK_ROWS / SK_GROUPS; i0 += 8) {
+    float a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {                                    // eight independent loads in flight
+      const int r = (i0 + u) * SK_GROUPS + grp;
+      a[u] = r < rows ? A[(k0 + r) * lda + mc] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float* x = xs + ((i0 + u) * SK_GROUPS + grp) * SK_MAXN;
+#pragma unroll
+      for (int j = 0; j < SK_MAXN; ++j) acc[j] = fmaf(a[u], x[j], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < SK_MAXN; ++j) red[grp][mi][j] = acc[j];
+  __syncthreads();
+  if (grp != 0 || m >= M) return;
+  float* o = part + ((int64_t)blockIdx.x * M + m) * N;
+#pragma unroll
+  for (int j = 0; j < SK_MAXN; ++j) {
+    if (j < N) {
+      float v = red[0][mi][j];
+#pragma unroll
+      for (int g2 = 1; g2 < SK_GROUPS; ++g2) v += red[g2][mi][j];
+      o[j] = v;
+    }
+  }
+}
+
 // Planning shared by the dry (workspace query) and the real call.
 struct TcPlan { int bn, gm, gn, ksplit; int64_t k_chunk; };
 static TcPlan tc_plan(int M, int N, int64_t K, GemmMode mode, bool want_stats) {
@@ -947,6 +1002,19 @@ static TcPlan tc_plan(int M, int N, int64_t K, GemmMode mode, bool want_stats) {
 }
 
 static int gemm_tc(const GemmArgs& a, GemmMode mode, Arena& ws, float* stat_part, int* stat_nparts, cudaStream_t st) {
+  static const bool skinny_on = !(getenv("YOLAT_TC_SKINNY") && getenv("YOLAT_TC_SKINNY")[0] == '0');
+  if (skinny_on && mode == GEMM_TN && a.N <= SK_MAXN && a.N > 0 && a.K > 0 && !a.a_sc && !a.b_sc && !stat_nparts) {
+    const int nsplit = (int)cdiv(a.K, SK_ROWS);
+    float* part = ws.take((int64_t)nsplit * a.M * a.N);
+    if (ws.dry()) return YOLAT_OK;
+    if (ws.overflow) return YOLAT_ERR_WORKSPACE;
+    k_tn_skinny<<<dim3((unsigned)nsplit, (unsigned)cdiv(a.M, 64)), 64 * SK_GROUPS, 0, st>>>(a.A, a.lda, a.B, a.ldb, a.M, a.N, a.K, part);
+    YOLAT_CHECK_LAUNCH();
+    k_splitk_sum_deep<<<(unsigned)cdiv((int64_t)a.M * a.N, 32), dim3(32, 32), 0, st>>>(part, nsplit, a.M, a.N, a.bias, a.C, a.ldc,
+                                                                                  a.accumulate);
+    YOLAT_CHECK_LAUNCH();
+    return YOLAT_OK;
+  }
   const TcPlan pl = tc_plan(a.M, a.N, a.K, mode, stat_nparts != nullptr);
   // Wave quantisation: one CTA per SM walks the tile list, so 157 row tiles cost two full passes for 1.06 passes of work
   // (dx = dz W of the fusion block: M = 20000, N = 128).  When a short tail spills over the last full wave, the rows of

@@ -124,36 +124,53 @@ __global__ void k_fusemax_bwd_apply(float* __restrict__ z, int64_t M, int F, con
   z[idx] = sc * (dy - bstat[c] - (zz - mean) * invstd * bstat[F + c]);
 }
 
-// Same, four columns per thread (F % 4 == 0, 16-byte aligned rows): 128-bit loads / stores, one row look-up per thread.
-__global__ void k_fusemax_bwd_apply4(float* __restrict__ z, int64_t M, int F4, const int32_t* __restrict__ seg_of_row,
-                                     const float* __restrict__ gp, int64_t ldg, const int32_t* __restrict__ arg,
-                                     int64_t lda, const float* __restrict__ stat, const float* __restrict__ bstat) {
-  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (idx >= M * F4) return;
-  const int64_t n = idx / F4;
-  const int c = (int)(idx - n * F4) * 4;
+// Same, four columns x four rows per thread (F % 4 == 0, 16-byte aligned rows): 128-bit loads / stores, the six
+// per-column parameter vectors are loaded once per thread and the four rows' loads are all in flight together.
+constexpr int FMB_ROWS = 4;
+__global__ void __launch_bounds__(256) k_fusemax_bwd_apply4(float* __restrict__ z, int64_t M, int F4,
+                                                            const int32_t* __restrict__ seg_of_row,
+                                                            const float* __restrict__ gp, int64_t ldg,
+                                                            const int32_t* __restrict__ arg, int64_t lda,
+                                                            const float* __restrict__ stat, const float* __restrict__ bstat) {
+  const int cg = blockIdx.y * 64 + (threadIdx.x & 63);              // column group (4 columns)
+  const int64_t n0 = ((int64_t)blockIdx.x * 4 + (threadIdx.x >> 6)) * FMB_ROWS;
+  if (cg >= F4 || n0 >= M) return;
+  const int c = cg * 4;
   const int F = F4 * 4;
   const float4 sc = __ldg(reinterpret_cast<const float4*>(stat + c)), sh = __ldg(reinterpret_cast<const float4*>(stat + F + c));
   const float4 mean = __ldg(reinterpret_cast<const float4*>(stat + 2 * F + c));
   const float4 invstd = __ldg(reinterpret_cast<const float4*>(stat + 3 * F + c));
   const float4 m1 = __ldg(reinterpret_cast<const float4*>(bstat + c)), m2 = __ldg(reinterpret_cast<const float4*>(bstat + F + c));
-  float4* zp = reinterpret_cast<float4*>(z + n * F + c);
-  const float4 zz = *zp;
-  const int32_t s = __ldg(seg_of_row + n);
-  float4 dy = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (s >= 0) {
-    const int4 a = __ldg(reinterpret_cast<const int4*>(arg + (int64_t)s * lda + c));
-    const int32_t nn = (int32_t)n;
-    if (a.x == nn || a.y == nn || a.z == nn || a.w == nn) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gp + (int64_t)s * ldg + c));
-      if (a.x == nn && fmaf(zz.x, sc.x, sh.x) > 0.f) dy.x = g.x;
-      if (a.y == nn && fmaf(zz.y, sc.y, sh.y) > 0.f) dy.y = g.y;
-      if (a.z == nn && fmaf(zz.z, sc.z, sh.z) > 0.f) dy.z = g.z;
-      if (a.w == nn && fmaf(zz.w, sc.w, sh.w) > 0.f) dy.w = g.w;
-    }
+  float4 zz[FMB_ROWS];
+  int32_t sg[FMB_ROWS];
+  int4 a[FMB_ROWS];
+#pragma unroll
+  for (int i = 0; i < FMB_ROWS; ++i) {
+    const int64_t n = n0 + i;
+    const bool in = n < M;
+    zz[i] = in ? *reinterpret_cast<const float4*>(z + n * F + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sg[i] = in ? __ldg(seg_of_row + n) : -1;
   }
-  *zp = make_float4(sc.x * (dy.x - m1.x - (zz.x - mean.x) * invstd.x * m2.x), sc.y * (dy.y - m1.y - (zz.y - mean.y) * invstd.y * m2.y),
-                    sc.z * (dy.z - m1.z - (zz.z - mean.z) * invstd.z * m2.z), sc.w * (dy.w - m1.w - (zz.w - mean.w) * invstd.w * m2.w));
+#pragma unroll
+  for (int i = 0; i < FMB_ROWS; ++i)
+    a[i] = sg[i] >= 0 ? __ldg(reinterpret_cast<const int4*>(arg + (int64_t)sg[i] * lda + c)) : make_int4(-1, -1, -1, -1);
+#pragma unroll
+  for (int i = 0; i < FMB_ROWS; ++i) {
+    const int64_t n = n0 + i;
+    if (n >= M) break;
+    const int32_t nn = (int32_t)n;
+    float4 dy = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a[i].x == nn || a[i].y == nn || a[i].z == nn || a[i].w == nn) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gp + (int64_t)sg[i] * ldg + c));
+      if (a[i].x == nn && fmaf(zz[i].x, sc.x, sh.x) > 0.f) dy.x = g.x;
+      if (a[i].y == nn && fmaf(zz[i].y, sc.y, sh.y) > 0.f) dy.y = g.y;
+      if (a[i].z == nn && fmaf(zz[i].z, sc.z, sh.z) > 0.f) dy.z = g.z;
+      if (a[i].w == nn && fmaf(zz[i].w, sc.w, sh.w) > 0.f) dy.w = g.w;
+    }
+    *reinterpret_cast<float4*>(z + n * F + c) =
+        make_float4(sc.x * (dy.x - m1.x - (zz[i].x - mean.x) * invstd.x * m2.x), sc.y * (dy.y - m1.y - (zz[i].y - mean.y) * invstd.y * m2.y),
+                    sc.z * (dy.z - m1.z - (zz[i].z - mean.z) * invstd.z * m2.z), sc.w * (dy.w - m1.w - (zz[i].w - mean.w) * invstd.w * m2.w));
+  }
 }
 
 // ---- CrossEntropyLoss (mean) -----------------------------------------------------------------------
@@ -267,7 +284,8 @@ int fusemax_bwd_apply_launch(float* z, int64_t M, int F, const int32_t* seg_of_r
                    ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(gp) | reinterpret_cast<uintptr_t>(arg) |
                      reinterpret_cast<uintptr_t>(stat) | reinterpret_cast<uintptr_t>(bstat)) & 15u) == 0;
   if (vec) {
-    k_fusemax_bwd_apply4<<<(unsigned)cdiv(M * (F / 4), 256), 256, 0, st>>>(z, M, F / 4, seg_of_row, gp, ldg, arg, lda, stat, bstat);
+    k_fusemax_bwd_apply4<<<dim3((unsigned)cdiv(M, 4 * FMB_ROWS), (unsigned)cdiv(F / 4, 64)), 256, 0, st>>>(z, M, F / 4, seg_of_row, gp,
+                                                                                                           ldg, arg, lda, stat, bstat);
     YOLAT_CHECK_LAUNCH();
     return YOLAT_OK;
   }

@@ -105,7 +105,7 @@ class GP2ConvFn(torch.autograd.Function):
         (w1, b1, g1, be1, w2, b2, g2, be2, wr, br, wn, bnode, gn, ben) = params
         (rm1, rv1, nbt1, rm2, rv2, nbt2, rmn, rvn, nbtn) = ctx.buffers
         N, E, Cin, Cn, C_ = ctx.dims
-        g_out, g_xn = L.f32c(g_out), L.f32c(g_xn)
+        g_out, g_xn = L.f32rows(g_out), L.f32rows(g_xn)     # column slices of a cat's gradient: no copy, pitch = ld
         P = L.Gp2Params(L.ptr(w1), L.ptr(b1), _bn_struct(g1, be1, rm1, rv1, None),
                         L.ptr(w2), L.ptr(b2), _bn_struct(g2, be2, rm2, rv2, None),
                         L.ptr(wr), L.ptr(br),
@@ -213,7 +213,7 @@ class MLPStageFn(torch.autograd.Function):
         flags = ctx.flags
         M, K = x.shape
         Nout = w.shape[0]
-        gy = L.f32c(gy)
+        gy = L.f32rows(gy)
         rm, rv, _ = ctx.buffers if ctx.buffers is not None else (None, None, None)
         bn = _bn_struct(gamma, beta, rm, rv, None) if flags & BN else None
         dx = torch.empty_like(x) if ctx.needs_input_grad[2] else None
@@ -265,7 +265,7 @@ class SegmentMeanFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        g = L.f32c(g)
+        g = L.f32rows(g)
         M, Cc = ctx.shape
         d = torch.zeros(M, Cc, dtype=torch.float32, device=g.device)   # rows with an out-of-range index keep 0
         L.check(L.lib().yolat_segment_mean_bwd(g.data_ptr(), g.stride(0), M, Cc, ctx.seg.ptr(), ctx.seg.S, d.data_ptr(),
@@ -291,7 +291,7 @@ class SegmentMaxFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (arg,) = ctx.saved_tensors
-        g = L.f32c(g)
+        g = L.f32rows(g)
         M, Cc = ctx.shape
         d = torch.empty(M, Cc, dtype=torch.float32, device=g.device)
         L.check(L.lib().yolat_segment_max_bwd(g.data_ptr(), g.stride(0), M, Cc, ctx.seg.S, arg.data_ptr(), d.data_ptr(),
@@ -342,7 +342,7 @@ class FuseMaxFn(torch.autograd.Function):
         seg = ctx.seg
         M, K = feats.shape
         F_ = w.shape[0]
-        gp = L.f32c(gp)
+        gp = L.f32rows(gp)
         rm, rv, _ = ctx.buffers
         bn = _bn_struct(gamma, beta, rm, rv, None)
         dfeats = torch.empty_like(feats) if ctx.needs_input_grad[3] else None
