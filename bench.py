@@ -190,6 +190,25 @@ def ncu_traffic():
         return json.load(f).get('dram_bytes_per_launch')
 
 
+def ncu_gemm():
+    """Tensor-pipe activity of the three fusion products from the committed `ncu --set full` capture
+    (profiles/r2_z_gemm_ncu.json): per operand layout, the mean over the full-size launches of the capture."""
+    p = os.path.join(ROOT, 'profiles', 'r2_z_gemm_ncu.json')
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        rep = json.load(f)
+    out = {'file': 'profiles/r2_z_gemm_ncu.json'}
+    for mode, name in ((0, 'NT'), (1, 'NN'), (2, 'TN')):
+        ks = [k for k in rep['kernels'] if 'k_tc_gemm_ws<%d,' % mode in k['Kernel Name'] and int(k['launch__grid_size']) >= 140]
+        if ks:
+            out[name] = {
+                'tensor_subpipe_active_pct': sum(float(k['sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active']) for k in ks) / len(ks),
+                'tf32_ops_pct_of_peak': sum(float(k['sm__ops_path_tensor_src_tf32_dst_fp32.sum.pct_of_peak_sustained_elapsed']) for k in ks) / len(ks),
+                'us': sum(float(k['gpu__time_duration.sum']) for k in ks) / len(ks)}
+    return out
+
+
 def edge_bytes(N, E, Cin, Cn, C):
     """Algorithmic bytes of one GraphConv('attr_edge_gp2') forward: x + edge_index (int64 as
     delivered) + e_attr + out, plus the node branch x_node + x_node_out."""
@@ -479,7 +498,9 @@ def main():
                          'frac_vs_bf16_sustained': flops / (gms * 1e-3) / 1e12 / tf_sust,
                          'frac_vs_3xtf32_peak': flops / (gms * 1e-3) / 1e12 / peak_3xtf32}
         nt = gem['NT y = x W^T']
-        roof_mlp = {'bound': 'tensor', 'kernel': 'tc::k_tc_gemm_ws (persistent warp-specialised tcgen05 GEMM, TMEM accumulators)',
+        roof_mlp = {'bound': 'tensor', 'kernel': 'tc::k_tc_gemm_ws<MODE,128,fast,TMA> (persistent warp-specialised tcgen05 GEMM, TMEM '
+                                                 'accumulators, operands by cp.async.bulk.tensor loads + in-place hi/lo split, C by TMA stores)',
+                    'ncu': ncu_gemm(),
                     'shape': {'M': M_, 'K': K_, 'N': N_}, 'flops': flops, 'ms': nt['ms'], 'achieved': nt['tflops'],
                     'unit': 'TFLOP/s', 'peak': tf_sust, 'frac': nt['frac_vs_bf16_sustained'],
                     'mma': '3xTF32: three tcgen05.mma.kind::tf32 per fp32-accurate product (hi*hi + hi*lo + lo*hi)',

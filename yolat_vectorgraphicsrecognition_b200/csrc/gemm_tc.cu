@@ -1022,11 +1022,11 @@ static int gemm_tc(const GemmArgs& a, GemmMode mode, Arena& ws, float* stat_part
   // Row-disjoint outputs: bias / accumulate keep their meaning; not for dW (rows are the reduction) nor when the
   // epilogue has to deliver column statistics of the whole matrix.
   static const bool tail_split = !(getenv("YOLAT_TC_TAIL") && getenv("YOLAT_TC_TAIL")[0] == '0');
-  if (tail_split && mode != GEMM_TN && !stat_nparts && pl.ksplit == 1 && a.K >= 8 * tc::BK) {
+  if (tail_split && mode != GEMM_TN && !stat_nparts && pl.ksplit == 1 && a.K >= 32 * tc::BK) {   // long reductions only
     const int64_t tiles = (int64_t)pl.gm * pl.gn;
     const int64_t full = tiles / kNumSMs * kNumSMs;
     const int gm_main = (int)(full / pl.gn);
-    if (full > 0 && tiles - full > 0 && (tiles - full) * 4 <= kNumSMs && gm_main > 0 && gm_main < pl.gm) {
+    if (full > 0 && tiles - full > 0 && (tiles - full) * 8 <= kNumSMs && gm_main > 0 && gm_main < pl.gm) {
       GemmArgs head = a, tail = a;
       head.M = gm_main * tc::BM;
       tail.M = a.M - head.M;
