@@ -45,9 +45,11 @@ def parse():
     ap.add_argument('--graphs', type=int, default=0, help='graphs per rank per step (0 = the workload default)')
     ap.add_argument('--global-batch', type=int, default=0,
                     help='BASELINE config 4: total graphs per step, split across the ranks (strong scaling)')
-    ap.add_argument('--collective', choices=('overlap', 'single'), default='overlap',
-                    help='N > 1: overlap = head-bucket all-reduce under the backward + the remainder after it; single = one '
-                         'all-reduce after the backward')
+    ap.add_argument('--collective', choices=('auto', 'symm', 'overlap', 'single'), default='auto',
+                    help='N > 1: symm = one in-place symmetric-memory all-reduce (multimem / two-shot) after the backward; '
+                         'overlap = NCCL head-bucket all-reduce under the backward + the remainder after it; single = one '
+                         'NCCL all-reduce after the backward; auto = symm from 4 ranks up when every rank can set it up (measured '
+                         'cross-over), else overlap')
     ap.add_argument('--mode', default='graph', choices=['graph', 'eager'],
                     help='graph: the step is replayed as one CUDA graph (GraphedStep); eager: launched from Python')
     ap.add_argument('--cpu-steps', type=int, default=8, help='timed steps of the cpu_baseline leg')
@@ -253,7 +255,8 @@ def main():
     # branch of the step graph); --collective single reduces the whole buffer once at the end of the backward.
     sync = None
     if world > 1:
-        sync = dp.OverlappedGradSync(model, overlap=args.collective == 'overlap', side_stream=args.mode == 'graph')
+        sync = dp.OverlappedGradSync(model, overlap=args.collective in ('overlap', 'auto'), side_stream=args.mode == 'graph',
+                                     symmetric='auto' if args.collective == 'auto' else args.collective == 'symm')
 
     def eager_step(batch):
         for p in params:
@@ -323,8 +326,11 @@ def main():
             plain(resident)
         ms_plain = timed(plain, resident, args.steps)
         sync.enabled = True
-        collective = {'op': 'ncclAllReduce(sum) of the flat fp32 gradient buffer (written in place by the backward kernels), '
-                            'captured in the step graph; schedule: %s' % args.collective,
+        how = ('torch.ops.symm_mem.%s over the symmetric flat buffer, one kernel after the backward' % sync._symm_op) if sync.symmetric \
+            else ('ncclAllReduce, schedule: %s' % ('overlap' if sync.overlap else 'single'))
+        collective = {'op': 'all-reduce (mean) of the flat fp32 gradient buffer (written in place by the backward kernels), '
+                            'captured in the step graph; %s' % how,
+                      'requested': args.collective, 'symmetric_memory': bool(sync.symmetric), 'symm_error': sync._symm_error,
                       'bytes': 4 * sync.numel, 'overlapped_bytes': sync.overlapped_bytes,
                       'exposed_bytes': sync.exposed_bytes, 'exposed_us': (ms - ms_plain) * 1e3,
                       'ms_per_step_without_collective': ms_plain, 'views_adopted': not sync.copy_mode}

@@ -75,9 +75,26 @@ def _worker(rank, world, port, out):
         torch.cuda.synchronize()
         err_side = float((sync.flat - want).abs().max() / want.abs().max())
         adopted = adopted and all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(sync.params, sync.views))
+        sync.close()
+        step.release()
+        del step
+        # ... and the symmetric-memory exchange (one in-place multimem / two-shot kernel over the flat buffer), eager and
+        # captured -- when the box cannot set it up every rank falls back to NCCL and the numbers must still be right
+        sync = dp.OverlappedGradSync(model, symmetric=True, side_stream=True)
+        symm = bool(sync.symmetric)
+        for p in model.parameters():
+            p.grad = None
+        crit(model(shards[rank], None), shards[rank])['loss'].backward()
+        err_symm_eager = float((sync.finish() - want).abs().max() / want.abs().max())
+        step = GraphedStep(model, crit, extra=sync.finish)
+        step(shards[rank])
+        step(shards[rank])
+        torch.cuda.synchronize()
+        err_symm = float((sync.flat - want).abs().max() / want.abs().max())
         if rank == 0:
             torch.save(dict(err_eager=err_eager, err_graph=err_graph, err_side=err_side, adopted=adopted,
-                            overlapped=overlapped, total=total), out)
+                            overlapped=overlapped, total=total, symm=symm, symm_op=sync._symm_op, symm_error=sync._symm_error,
+                            err_symm=err_symm, err_symm_eager=err_symm_eager), out)
         sync.close()
         step.release()
         del step
@@ -110,3 +127,5 @@ def test_overlapped_grad_sync_nccl_world2(tmp_path):
     assert res['adopted']
     assert res['err_eager'] < 1e-6 and res['err_graph'] < 1e-6 and res['err_side'] < 1e-6, res
     assert res['overlapped'] > 0.8 * res['total']
+    print('symmetric memory:', res['symm'], res['symm_op'], res['symm_error'])
+    assert res['err_symm'] < 1e-6 and res['err_symm_eager'] < 1e-6, res

@@ -82,6 +82,13 @@ class OverlappedGradSync(object):
     work issued from autograd hooks inside a capture fails with cudaErrorStreamCaptureIsolation or hangs on torch 2.11 /
     NCCL 2.28; tools/nccl_capture_probe.py and tools/nccl_hang_probe.py list what captures cleanly.)
     `overlap=False` drops the hooks: one collective over the whole buffer in `finish()`.
+    `symmetric=True` (NCCL groups on one NVSwitch node) allocates the flat buffer as torch symmetric memory and reduces
+    it in `finish()` with ONE in-place kernel over peer / multicast addresses (`symm_mem.multimem_all_reduce_` when the
+    fabric supports multicast -- the reduction happens in the switch --, else `two_shot_all_reduce_`): a 6 MB buffer
+    is latency-bound, and this path has a third of NCCL's latency and, unlike an overlapped NCCL kernel, never holds
+    SMs while the persistent compute kernels (one CTA per SM) are running.  `symmetric='auto'` selects it from 4 ranks up
+    (measured cross-over).  All ranks agree on availability with one
+    all-reduce; when any rank cannot set it up, every rank silently keeps the NCCL schedule (`self.symmetric` tells).
 
     BatchNorm statistics stay rank-local (DDP-default semantics).  Gradients must be re-created every step
     (`zero_grad(set_to_none=True)`, what GraphedStep does): an existing `p.grad` makes autograd accumulate in place
@@ -90,17 +97,26 @@ class OverlappedGradSync(object):
     """
 
     def __init__(self, model, group=None, early_prefixes=('prediction_cls',), overlap=True, async_early=True,
-                 side_stream=False):
+                 side_stream=False, symmetric=False):
         from . import ops
         self.overlap, self.async_early, self.side_stream = bool(overlap), bool(async_early), bool(side_stream)
         self._side, self._side_pending = None, False
+        self.symmetric, self._symm_group, self._symm_op, self._symm_error = False, None, None, None
         self._avg = None
         named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
         self.params = [p for _, p in named]
         self.group = group
         p0 = self.params[0]
         self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=p0.device)
+        self.flat = None
+        # 'auto': measured on B200 / NVSwitch with this 6.45 MB buffer -- the multimem kernel moves 1 / world of the bytes
+        # per rank, so it beats NCCL's overlapped schedule from 4 ranks up (8 ranks: 43 vs 83 us exposed; 2 ranks: 74 vs 56)
+        if symmetric == 'auto':
+            symmetric = dist.is_initialized() and self.world() >= 4
+        if symmetric:
+            self._try_symmetric(p0.device)
+        if self.flat is None:
+            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=p0.device)
         self.offsets, off = [], 0
         for p in self.params:
             self.offsets.append(off)
@@ -119,6 +135,8 @@ class OverlappedGradSync(object):
         self.enabled = True           # False: the hooks do nothing (steps that must not communicate, e.g. an A/B timing)
         self._count = 0
         self._work = None
+        if self.symmetric:
+            self.overlap = False              # one in-place kernel in finish(): nothing to issue from hooks
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.early_params] if self.overlap else []
         if not self.overlap:
             self.split = self.numel           # one bucket, reduced in finish()
@@ -127,6 +145,36 @@ class OverlappedGradSync(object):
 
     def world(self):
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def _try_symmetric(self, device):
+        """Flat buffer in symmetric memory + rendezvous; every rank must succeed or every rank falls back."""
+        if not (dist.is_initialized() and self.world() > 1 and device.type == 'cuda'
+                and dist.get_backend(self.group) == 'nccl'):
+            return
+        ok, flat, full, op = 0, None, None, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            pg = self.group if self.group is not None else dist.group.WORLD
+            padded = (self.numel + 4095) // 4096 * 4096            # the kernels want 16-byte multiples per rank
+            full = symm_mem.empty(padded, dtype=torch.float32, device=device)
+            full.zero_()
+            hdl = symm_mem.rendezvous(full, pg)
+            op = 'multimem_all_reduce_' if int(getattr(hdl, 'multicast_ptr', 0) or 0) != 0 else 'two_shot_all_reduce_'
+            if not hasattr(torch.ops.symm_mem, op):
+                raise RuntimeError('torch.ops.symm_mem.%s is missing' % op)
+            flat = full.narrow(0, 0, self.numel)
+            ok = 1
+        except Exception as e:        # noqa: BLE001 -- any set-up failure means "use NCCL"
+            self._symm_error = '%s: %s' % (type(e).__name__, str(e).splitlines()[0][:200] if str(e) else '')
+        agree = torch.tensor([ok, 1 if op == 'multimem_all_reduce_' else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.group)
+        if int(agree[0].item()) != 1:
+            return
+        pg = self.group if self.group is not None else dist.group.WORLD
+        self._symm_full, self.flat = full, flat
+        self._symm_group = pg.group_name
+        self._symm_op = 'multimem_all_reduce_' if int(agree[1].item()) == 1 else 'two_shot_all_reduce_'
+        self.symmetric = True
 
     def _op(self):
         """ncclAvg folds the 1 / world scaling into the collective (no separate kernel over the buffer); gloo has no AVG."""
@@ -191,6 +239,10 @@ class OverlappedGradSync(object):
                 dist.all_reduce(self.flat, op=self._op(), group=self.group)
             for p, v in zip(self.params, self.views):
                 p.grad = v
+        elif world > 1 and self.symmetric:
+            getattr(torch.ops.symm_mem, self._symm_op)(self._symm_full, 'sum', self._symm_group)
+            self.flat.mul_(1.0 / world)
+            return self.flat
         elif world > 1:
             if self.split > 0:
                 dist.all_reduce(self.flat.narrow(0, 0, self.split), op=self._op(), group=self.group)
