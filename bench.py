@@ -45,11 +45,11 @@ def parse():
     ap.add_argument('--graphs', type=int, default=0, help='graphs per rank per step (0 = the workload default)')
     ap.add_argument('--global-batch', type=int, default=0,
                     help='BASELINE config 4: total graphs per step, split across the ranks (strong scaling)')
-    ap.add_argument('--collective', choices=('auto', 'symm', 'overlap', 'single'), default='auto',
-                    help='N > 1: symm = one in-place symmetric-memory all-reduce (multimem / two-shot) after the backward; '
+    ap.add_argument('--collective', choices=('auto', 'symm', 'symm-single', 'overlap', 'single'), default='auto',
+                    help='N > 1: symm = in-place symmetric-memory all-reduce (multimem / two-shot), head bucket under the backward + '
+                         'remainder after it; symm-single = one such call after the backward; '
                          'overlap = NCCL head-bucket all-reduce under the backward + the remainder after it; single = one '
-                         'NCCL all-reduce after the backward; auto = symm from 4 ranks up when every rank can set it up (measured '
-                         'cross-over), else overlap')
+                         'NCCL all-reduce after the backward; auto = symm when every rank can set it up, else overlap')
     ap.add_argument('--mode', default='graph', choices=['graph', 'eager'],
                     help='graph: the step is replayed as one CUDA graph (GraphedStep); eager: launched from Python')
     ap.add_argument('--cpu-steps', type=int, default=8, help='timed steps of the cpu_baseline leg')
@@ -255,8 +255,8 @@ def main():
     # branch of the step graph); --collective single reduces the whole buffer once at the end of the backward.
     sync = None
     if world > 1:
-        sync = dp.OverlappedGradSync(model, overlap=args.collective in ('overlap', 'auto'), side_stream=args.mode == 'graph',
-                                     symmetric='auto' if args.collective == 'auto' else args.collective == 'symm')
+        sync = dp.OverlappedGradSync(model, overlap=args.collective in ('overlap', 'auto', 'symm'), side_stream=args.mode == 'graph',
+                                     symmetric='auto' if args.collective == 'auto' else args.collective.startswith('symm'))
 
     def eager_step(batch):
         for p in params:
@@ -326,7 +326,8 @@ def main():
             plain(resident)
         ms_plain = timed(plain, resident, args.steps)
         sync.enabled = True
-        how = ('torch.ops.symm_mem.%s over the symmetric flat buffer, one kernel after the backward' % sync._symm_op) if sync.symmetric \
+        how = ('torch.ops.symm_mem.%s over the symmetric flat buffer, %s' % (sync._symm_op, 'head bucket on a side stream under the '
+               'backward + remainder after it' if sync.overlap else 'one kernel after the backward')) if sync.symmetric \
             else ('ncclAllReduce, schedule: %s' % ('overlap' if sync.overlap else 'single'))
         collective = {'op': 'all-reduce (mean) of the flat fp32 gradient buffer (written in place by the backward kernels), '
                             'captured in the step graph; %s' % how,

@@ -80,7 +80,7 @@ def _worker(rank, world, port, out):
         del step
         # ... and the symmetric-memory exchange (one in-place multimem / two-shot kernel over the flat buffer), eager and
         # captured -- when the box cannot set it up every rank falls back to NCCL and the numbers must still be right
-        sync = dp.OverlappedGradSync(model, symmetric=True, side_stream=True)
+        sync = dp.OverlappedGradSync(model, symmetric=True, side_stream=True)      # head bucket on a side stream + remainder
         symm = bool(sync.symmetric)
         for p in model.parameters():
             p.grad = None
@@ -91,10 +91,19 @@ def _worker(rank, world, port, out):
         step(shards[rank])
         torch.cuda.synchronize()
         err_symm = float((sync.flat - want).abs().max() / want.abs().max())
+        symm_op, symm_error = sync._symm_op, sync._symm_error
+        sync.close()
+        step.release()
+        del step
+        sync = dp.OverlappedGradSync(model, symmetric=True, overlap=False)             # one call after the backward
+        step = GraphedStep(model, crit, extra=sync.finish)
+        step(shards[rank])
+        torch.cuda.synchronize()
+        err_symm_single = float((sync.flat - want).abs().max() / want.abs().max())
         if rank == 0:
             torch.save(dict(err_eager=err_eager, err_graph=err_graph, err_side=err_side, adopted=adopted,
-                            overlapped=overlapped, total=total, symm=symm, symm_op=sync._symm_op, symm_error=sync._symm_error,
-                            err_symm=err_symm, err_symm_eager=err_symm_eager), out)
+                            overlapped=overlapped, total=total, symm=symm, symm_op=symm_op, symm_error=symm_error,
+                            err_symm=max(err_symm, err_symm_single), err_symm_eager=err_symm_eager), out)
         sync.close()
         step.release()
         del step

@@ -86,8 +86,8 @@ class OverlappedGradSync(object):
     it in `finish()` with ONE in-place kernel over peer / multicast addresses (`symm_mem.multimem_all_reduce_` when the
     fabric supports multicast -- the reduction happens in the switch --, else `two_shot_all_reduce_`): a 6 MB buffer
     is latency-bound, and this path has a third of NCCL's latency and, unlike an overlapped NCCL kernel, never holds
-    SMs while the persistent compute kernels (one CTA per SM) are running.  `symmetric='auto'` selects it from 4 ranks up
-    (measured cross-over).  All ranks agree on availability with one
+    SMs while the persistent compute kernels (one CTA per SM) are running.  `symmetric='auto'` selects it whenever it can be
+    set up; with `overlap=True` the head bucket is reduced by the same kernel on a side stream under the backward.  All ranks agree on availability with one
     all-reduce; when any rank cannot set it up, every rank silently keeps the NCCL schedule (`self.symmetric` tells).
 
     BatchNorm statistics stay rank-local (DDP-default semantics).  Gradients must be re-created every step
@@ -109,10 +109,11 @@ class OverlappedGradSync(object):
         p0 = self.params[0]
         self.numel = sum(p.numel() for p in self.params)
         self.flat = None
-        # 'auto': measured on B200 / NVSwitch with this 6.45 MB buffer -- the multimem kernel moves 1 / world of the bytes
-        # per rank, so it beats NCCL's overlapped schedule from 4 ranks up (8 ranks: 43 vs 83 us exposed; 2 ranks: 74 vs 56)
+        # 'auto': measured on B200 / NVSwitch with this 6.45 MB buffer -- exposed time per step, NCCL overlapped vs
+        # symmetric memory (one call after the backward) vs symmetric memory with the head bucket on a side stream:
+        # 2 ranks 56 / 74 / 37 us, 8 ranks 83 / 44 / see DESIGN.md 3.5.  The overlapped symmetric schedule wins everywhere.
         if symmetric == 'auto':
-            symmetric = dist.is_initialized() and self.world() >= 4
+            symmetric = dist.is_initialized() and self.world() >= 2
         if symmetric:
             self._try_symmetric(p0.device)
         if self.flat is None:
@@ -136,7 +137,12 @@ class OverlappedGradSync(object):
         self._count = 0
         self._work = None
         if self.symmetric:
-            self.overlap = False              # one in-place kernel in finish(): nothing to issue from hooks
+            # the two kernel calls split the buffer at a 4096-element boundary at or after the bucket boundary (the
+            # multimem kernels want aligned, 16-byte-multiple slices); the few early-bucket elements below it simply
+            # travel with the second call
+            self._symm_split = min((self.split + 4095) // 4096 * 4096, self._symm_full.numel())
+            if self._symm_split >= self._symm_full.numel() or self.split >= self.numel:
+                self.overlap = False
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.early_params] if self.overlap else []
         if not self.overlap:
             self.split = self.numel           # one bucket, reduced in finish()
@@ -204,7 +210,16 @@ class OverlappedGradSync(object):
                 raise RuntimeError('OverlappedGradSync: an uncaptured collective is pending; call drain() before the capture')
             self._work.wait()
             self._work = None
-        if self.world() > 1 and self.split < self.numel:
+        if self.world() > 1 and self.split < self.numel and self.symmetric:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.flat.device)
+            self._side.wait_stream(torch.cuda.current_stream(self.flat.device))         # fork: the early grads are final
+            with torch.cuda.stream(self._side):
+                early = self._symm_full.narrow(0, self._symm_split, self._symm_full.numel() - self._symm_split)
+                getattr(torch.ops.symm_mem, self._symm_op)(early, 'sum', self._symm_group)
+                early.mul_(1.0 / self.world())
+            self._side_pending = True
+        elif self.world() > 1 and self.split < self.numel:
             early = self.flat.narrow(0, self.split, self.numel - self.split)
             if self.side_stream:
                 if self._side is None:
@@ -240,8 +255,10 @@ class OverlappedGradSync(object):
             for p, v in zip(self.params, self.views):
                 p.grad = v
         elif world > 1 and self.symmetric:
-            getattr(torch.ops.symm_mem, self._symm_op)(self._symm_full, 'sum', self._symm_group)
-            self.flat.mul_(1.0 / world)
+            late = self._symm_full.narrow(0, 0, self._symm_split) if self.overlap else self._symm_full
+            getattr(torch.ops.symm_mem, self._symm_op)(late, 'sum', self._symm_group)
+            late.mul_(1.0 / world)
+            self._join_side()
             return self.flat
         elif world > 1:
             if self.split > 0:
