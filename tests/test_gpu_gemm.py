@@ -82,7 +82,8 @@ def test_gemm_tma_edges():
     from yolat_vectorgraphicsrecognition_b200 import ops
     g = torch.Generator().manual_seed(21)
     for mode, M, N, K in ((1, 20000, 128, 1024), (0, 19000, 128, 320), (0, 4100, 100, 72), (1, 777, 36, 200),
-                          (2, 96, 40, 7001), (0, 300, 20, 44), (2, 128, 5, 20000), (2, 200, 8, 777), (2, 64, 1, 130)):
+                          (2, 96, 40, 7001), (0, 300, 20, 44), (2, 128, 5, 20000), (2, 200, 8, 777), (2, 64, 1, 130),
+                          (0, 20000, 64, 5), (0, 777, 192, 5), (0, 300, 20, 8), (0, 130, 256, 3)):
         a, b = _operands(mode, M, N, K, g)
         assert max_rel(ops.gemm(mode, a.cuda(), b.cuda()), _ref(mode, a, b)) < TOL, (mode, M, N, K)
     wide_a = torch.randn(3000, 256, generator=g).cuda()

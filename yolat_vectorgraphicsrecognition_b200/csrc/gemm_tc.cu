@@ -965,6 +965,66 @@ __global__ void __launch_bounds__(64 * SK_GROUPS) k_tn_skinny(const float* __res
   }
 }
 
+// ---- skinny reduction: y = x W^T + b with K <= 8 (the head GraphConv's Linear layers read 5 input features) ------------
+// A 128 x 64 x 32 tensor tile would be 84 % padding along K and its operands cannot be TMA-loaded (20-byte rows).  SIMT:
+// thread = 4 output columns of one row, W^T staged in shared memory as [K][N] (conflict-free float4 reads), the x row
+// is a broadcast.  A CTA walks SKN_ROWS rows and, on request, leaves the column statistics of its rows as one partial
+// [2][N] -- the same contract as the tensor-core epilogue.
+constexpr int SKN_ROWS = 128;
+__global__ void __launch_bounds__(256) k_nt_skinny(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                   int64_t ldb, const float* __restrict__ bias, float* __restrict__ C,
+                                                   int64_t ldc, int M, int N, int K, int accumulate, int c_vec,
+                                                   float* __restrict__ stat_part) {
+  __shared__ __align__(16) float wt[SK_MAXN * 256];       // [K][N]
+  __shared__ __align__(16) float red[2 * 1024];           // [2][lanes][N], lanes * N = 1024
+  const int tid = threadIdx.x;
+  const int cgs = N >> 2, lanes = 256 / cgs;
+  const int cg = tid % cgs, rl = tid / cgs;
+  const int c = cg * 4;
+  for (int i = tid; i < N * K; i += 256) wt[(i % K) * N + i / K] = B[(int64_t)(i / K) * ldb + (i % K)];
+  __syncthreads();
+  const int r0 = blockIdx.x * SKN_ROWS, r1 = min(M, r0 + SKN_ROWS);
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) b4 = make_float4(bias[c], bias[c + 1], bias[c + 2], bias[c + 3]);
+  float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = s4;
+  if (rl < lanes) {
+    for (int r = r0 + rl; r < r1; r += lanes) {
+      float4 v = b4;
+      const float* x = A + (int64_t)r * lda;
+#pragma unroll
+      for (int k = 0; k < SK_MAXN; ++k) {
+        if (k < K) {
+          const float xv = __ldg(x + k);
+          const float4 w = *reinterpret_cast<const float4*>(wt + k * N + c);
+          v.x = fmaf(xv, w.x, v.x); v.y = fmaf(xv, w.y, v.y); v.z = fmaf(xv, w.z, v.z); v.w = fmaf(xv, w.w, v.w);
+        }
+      }
+      s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+      q4.x = fmaf(v.x, v.x, q4.x); q4.y = fmaf(v.y, v.y, q4.y); q4.z = fmaf(v.z, v.z, q4.z); q4.w = fmaf(v.w, v.w, q4.w);
+      float* o = C + (int64_t)r * ldc + c;
+      if (c_vec) {
+        if (accumulate) { const float4 old = *reinterpret_cast<const float4*>(o); v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
+        *reinterpret_cast<float4*>(o) = v;
+      } else {
+        o[0] = accumulate ? o[0] + v.x : v.x; o[1] = accumulate ? o[1] + v.y : v.y;
+        o[2] = accumulate ? o[2] + v.z : v.z; o[3] = accumulate ? o[3] + v.w : v.w;
+      }
+    }
+  }
+  if (!stat_part) return;
+  if (rl < lanes) {
+    *reinterpret_cast<float4*>(red + (0 * lanes + rl) * N + c) = s4;
+    *reinterpret_cast<float4*>(red + (1 * lanes + rl) * N + c) = q4;
+  }
+  __syncthreads();
+  if (tid < N) {
+    float s = 0.f, q = 0.f;
+    for (int l = 0; l < lanes; ++l) { s += red[(0 * lanes + l) * N + tid]; q += red[(1 * lanes + l) * N + tid]; }
+    stat_part[((int64_t)blockIdx.x * 2 + 0) * N + tid] = s;
+    stat_part[((int64_t)blockIdx.x * 2 + 1) * N + tid] = q;
+  }
+}
+
 // Planning shared by the dry (workspace query) and the real call.
 struct TcPlan { int bn, gm, gn, ksplit; int64_t k_chunk; };
 static TcPlan tc_plan(int M, int N, int64_t K, GemmMode mode, bool want_stats) {
@@ -1012,6 +1072,16 @@ static int gemm_tc(const GemmArgs& a, GemmMode mode, Arena& ws, float* stat_part
     YOLAT_CHECK_LAUNCH();
     k_splitk_sum_deep<<<(unsigned)cdiv((int64_t)a.M * a.N, 32), dim3(32, 32), 0, st>>>(part, nsplit, a.M, a.N, a.bias, a.C, a.ldc,
                                                                                   a.accumulate);
+    YOLAT_CHECK_LAUNCH();
+    return YOLAT_OK;
+  }
+  if (skinny_on && mode == GEMM_NT && a.K > 0 && a.K <= SK_MAXN && a.N >= 16 && a.N <= 256 && a.N % 4 == 0 && !a.a_sc &&
+      !a.b_sc && a.M > 0) {
+    const int nb = (int)cdiv(a.M, SKN_ROWS);
+    if (stat_nparts) *stat_nparts = nb;                 // one partial per CTA (fits the cdiv(M, 128) * 4 the caller reserved)
+    if (ws.dry()) return YOLAT_OK;
+    const int c_vec = aligned16p(a.C) && (a.ldc % 4 == 0);
+    k_nt_skinny<<<nb, 256, 0, st>>>(a.A, a.lda, a.B, a.ldb, a.bias, a.C, a.ldc, a.M, a.N, (int)a.K, a.accumulate, c_vec, stat_part);
     YOLAT_CHECK_LAUNCH();
     return YOLAT_OK;
   }
