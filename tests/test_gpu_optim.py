@@ -66,8 +66,13 @@ def test_fused_adam_resumes_from_a_torch_adam_checkpoint_and_follows_the_schedul
 
 def test_fused_adam_is_capturable_in_the_step_graph():
     """GraphedStep(optimizer=FusedAdam): forward + loss + backward + Adam replayed as one graph.  The capture's warm-up
-    steps must not update anything (step counter == replays), and the captured step must follow a learning-rate change
-    made after the capture (hyper-parameters live in device memory): same trajectory as an eager torch.optim.Adam."""
+    steps must not update anything (step counter == replays == BatchNorm batches tracked), and the captured step must
+    follow a learning-rate change made after the capture (hyper-parameters live in device memory).
+
+    The reference is an eager torch.optim.Adam fed with the SAME gradients (copied out of the replayed step), so the
+    comparison isolates the optimizer arithmetic.  (Two independently trained copies diverge chaotically at the 1e-5
+    level within 8 steps: biases feeding a BatchNorm have mathematically-zero gradients, Adam turns their rounding noise
+    into lr-sized steps, and those feed back through the features.)"""
     import copy
     from yolat_vectorgraphicsrecognition_b200 import synth
     from yolat_vectorgraphicsrecognition_b200 import architecture3cc_rpn_gp_iter2 as arch
@@ -89,18 +94,15 @@ def test_fused_adam_is_capturable_in_the_step_graph():
             optim.param_groups[0]['lr'] = 2.5e-4
             ref_optim.param_groups[0]['lr'] = 2.5e-4
         losses.append(float(step(batch).detach()))
-        ref_optim.zero_grad(set_to_none=True)
-        crit(ref_model(batch, None), batch)['loss'].backward()
+        for pr, pm in zip(ref_model.parameters(), model.parameters()):
+            pr.grad = pm.grad.detach().clone()        # the gradients the replay just consumed
         ref_optim.step()
     assert losses[-1] < losses[0], losses
     assert float(optim.state_dict()['state'][0]['step']) == 8.0      # no hidden updates during the capture warm-up
+    for k, buf in model.named_buffers():
+        if k.endswith('num_batches_tracked'):
+            assert int(buf) == 8, (k, int(buf))                      # ... and no hidden BatchNorm updates either
     for (k, a), b in zip(model.named_parameters(), ref_model.parameters()):
         if a.dim() < 2:
-            continue      # biases feeding a BatchNorm have mathematically-zero gradients: Adam amplifies their rounding
-                          # noise to lr-sized steps, so 1-ulp differences between the two optimizers diverge there
-        # 8 Adam steps move a weight by up to ~8e-3; the two optimizers round differently by an ulp, and the noise-driven
-        # bias steps above feed that back through the features: 5e-5 is < 1 % of the distance travelled (measured 1-2.2e-5)
-        assert float((a.detach() - b.detach()).abs().max()) <= 5e-5 * max(1.0, float(b.detach().abs().max())), k
-    for (k, a), b in zip(model.named_buffers(), ref_model.buffers()):
-        # (the noise-driven bias steps shift the features by O(lr): the running statistics follow at that level)
-        assert float((a.double() - b.double()).abs().max()) <= 2e-3 * max(1.0, float(b.double().abs().max())), k
+            continue      # zero-gradient biases: m / sqrt(v) of pure rounding noise, decided by the last bit of either optimizer
+        assert float((a.detach() - b.detach()).abs().max()) <= 1e-6 * max(1.0, float(b.detach().abs().max())), k
