@@ -71,7 +71,8 @@ def _worker_overlap(rank, world, port, out):
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         model, grads = _shard_grads(rank)
-        sync = dp.OverlappedGradSync(model)
+        sync = dp.OverlappedGradSync(model, symmetric='auto')     # gloo / CPU: the symmetric-memory path must decline
+        assert not sync.symmetric and sync._symm_op is None
         # layout: model.parameters() order, the classifier head (final first in backward) is the contiguous tail
         n_head = sum(p.numel() for k, p in model.named_parameters() if k.startswith('prediction_cls'))
         assert sync.numel == 1613329 and sync.numel - sync.split == n_head and sync.overlapped_bytes == 4 * n_head

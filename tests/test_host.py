@@ -202,3 +202,19 @@ def test_fused_adam_has_no_cpu_path():
         FusedAdam([p], lr=-1.0)
     with pytest.raises(ValueError):
         FusedAdam([p], betas=(1.0, 0.999))
+
+
+def test_f32rows_keeps_column_slices():
+    """`_lib.f32rows`: what the backward of torch.cat(dim=1) hands to its producers (column slices of a wider matrix)
+    passes through with its pitch; anything else falls back to a contiguous fp32 copy."""
+    import torch
+    from yolat_vectorgraphicsrecognition_b200 import _lib as L
+    wide = torch.arange(60, dtype=torch.float32).reshape(5, 12)
+    sl = wide[:, 4:8]
+    assert L.f32rows(sl).data_ptr() == sl.data_ptr() and L.f32rows(sl).stride(0) == 12
+    assert L.f32rows(wide).data_ptr() == wide.data_ptr()
+    t = wide.t()                                         # column-major view: must be copied
+    assert L.f32rows(t).is_contiguous() and torch.equal(L.f32rows(t), t)
+    e = torch.ones(1, 1).expand(5, 4)                    # stride-0 broadcast (sum().backward()): must be copied
+    assert L.f32rows(e).is_contiguous()
+    assert L.f32rows(sl.double()).dtype == torch.float32
