@@ -273,6 +273,60 @@ int yolat_edge1_bwd(const float* w1, const yolat_bn* bn, int Cin, int C, const f
  * ---------------------------------------------------------------------------------------------- */
 int yolat_batch_offsets(int64_t* edge, int64_t E, int64_t* bbox_idx, int64_t N, const int64_t* tab, int64_t G, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Proposal enumeration of the reference Dataset on the device (Datasets/graph_dict3.py:309-789,
+ * SESYDFloorPlan._get_proposal with do_mixup off; csrc/proposals.cu).  One image per call.
+ *   in:  the image's graph as the Dataset's pickle holds it: pos [n_all,2] f64, is_control / is_super [n_all] u8,
+ *        connected components as CSR (cc_ptr [ncc+1], cc_idx [cc_total], original node ids), shape / super edges
+ *        [E,2] / [Es,2] int64 (original node ids) with their attribute rows [E,A] / [Es,As] f64, ground-truth boxes
+ *        [G,4] f64 + labels [G] int64; sampling_step = bbox_sampling_step, n_classes (label of "no object" =
+ *        n_classes - 1), normalize_bbox (graph_dict3.py:53).  All pointers are device pointers.
+ *   yolat_proposals_ws_bytes: workspace size in BYTES for these sizes (reads only the sizes); -1 = unsupported.
+ *   yolat_proposals_count:    everything up to the proposals' sizes; writes totals[YOLAT_PROP_TOTALS] (device int64):
+ *        node / shape-edge / super-edge / proposal counts of the outputs, the number of non-control nodes, an error
+ *        mask (YOLAT_PROP_ERR_*; the conditions under which the reference raises) and the first offending component.
+ *   yolat_proposals_fill:     writes the outputs (sized from totals by the caller) out of the same workspace.
+ *   out: pos [n,2] f64, is_super [n] u8, bbox_idx [n] int64, edge [e,2] / edge_super [es,2] int64, e_attr [e,A] /
+ *        e_attr_super [es,As] f64, labels / has_obj [B] int64, bbox / bbox_targets [B,4] f64, stat_feats [B,13] f64,
+ *        slice_pos / slice_edge / slice_super / slice_bbox [B+1] int64 (the subcluster_slice_* lists of :371-374),
+ *        cc_table [ncc,3] int64 = (first proposal, number of proposals, root proposal) of every component, from which
+ *        the caller builds the idxTree roots of :730-768.
+ * Proposals of one component are emitted in first-occurrence order of the reference's window walk (the reference's
+ * own order is CPython's `set` iteration order); everything else is the reference's output.
+ * ---------------------------------------------------------------------------------------------- */
+#define YOLAT_PROP_TOTALS 8
+#define YOLAT_PROP_T_NODES 0
+#define YOLAT_PROP_T_EDGES 1
+#define YOLAT_PROP_T_SUPER 2
+#define YOLAT_PROP_T_BOXES 3
+#define YOLAT_PROP_T_ERR 4
+#define YOLAT_PROP_T_ERR_CC 5
+#define YOLAT_PROP_T_NODES_IN 6
+#define YOLAT_PROP_ERR_ZERO_STEP 1ull    /* a component without x or y extent: np.arange(.., step 0) raises ValueError (:470-476) */
+#define YOLAT_PROP_ERR_NO_GT 2ull        /* 'cc has no intersect gt bbox' -> SystemExit (:574-576)              */
+#define YOLAT_PROP_ERR_NO_PROPOSAL 4ull  /* a component none of whose sets survives: np.argmax([]) raises (:728) */
+#define YOLAT_PROP_ERR_CONTROL_REF 8ull  /* an edge / component names a control point: o2n KeyError (:332-348)    */
+#define YOLAT_PROP_ERR_CC_OVERLAP 16ull  /* a node listed in two components (not a partition)                     */
+#define YOLAT_PROP_ERR_LIMIT 32ull       /* component > 2^20-2 nodes, > 2^23-1 edges, or too many grid lines       */
+#define YOLAT_PROP_ERR_INDEX 64ull       /* node id outside [0, n_all)                                            */
+typedef struct {
+  const double* pos; const uint8_t* is_control; const uint8_t* is_super; int64_t n_all;
+  const int64_t* cc_ptr; const int64_t* cc_idx; int64_t ncc; int64_t cc_total;
+  const int64_t* edge; const double* e_attr; int64_t E; int32_t A;
+  const int64_t* edge_super; const double* e_attr_super; int64_t Es; int32_t As;
+  const double* gt_bbox; const int64_t* gt_labels; int64_t G;
+  int32_t sampling_step; int32_t n_classes; int32_t normalize_bbox;
+} YolatProposalIn;
+typedef struct {
+  double* pos; uint8_t* is_super; int64_t* bbox_idx;
+  int64_t* edge; int64_t* edge_super; double* e_attr; double* e_attr_super;
+  int64_t* labels; int64_t* has_obj; double* bbox; double* bbox_targets; double* stat_feats;
+  int64_t* slice_pos; int64_t* slice_edge; int64_t* slice_super; int64_t* slice_bbox; int64_t* cc_table;
+} YolatProposalOut;
+int64_t yolat_proposals_ws_bytes(const YolatProposalIn* in);
+int yolat_proposals_count(const YolatProposalIn* in, void* ws, int64_t ws_bytes, int64_t* totals, void* stream);
+int yolat_proposals_fill(const YolatProposalIn* in, void* ws, int64_t ws_bytes, const YolatProposalOut* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

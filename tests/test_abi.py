@@ -54,3 +54,24 @@ def test_null_arguments_are_rejected(lib):
     assert lib.yolat_segments_build(None, 10, 2, None, None) == -1
     assert lib.yolat_mlp_fwd(None, 8, 4, 8, None, None, 8, None, 0, None, 8, None, 0, None, 0, None) == -1
     assert lib.yolat_softmax_xent_fwd(None, 17, 4, 17, None, None, None, None, 0, None) == -1
+
+
+def test_proposals_host_side(lib):
+    """Proposal enumeration (include/yolat_b200.h, last block): the workspace query is pure host code, the entry points
+    validate their arguments before touching the device."""
+    from yolat_vectorgraphicsrecognition_b200 import proposals as P
+    s = P.ProposalIn()
+    s.n_all, s.ncc, s.cc_total, s.E, s.A, s.Es, s.As, s.G = 5000, 300, 4000, 6000, 6, 500, 6, 40
+    s.sampling_step, s.n_classes, s.normalize_bbox = 5, 17, 1
+    small = lib.yolat_proposals_ws_bytes(ctypes.byref(s))
+    assert small > 300 * 441 * 8 * 13                                  # at least the per-candidate statistics
+    s.sampling_step = 10
+    assert lib.yolat_proposals_ws_bytes(ctypes.byref(s)) > small
+    s.sampling_step = 63                                               # more grid lines than the kernels hold
+    assert lib.yolat_proposals_ws_bytes(ctypes.byref(s)) == -1
+    s.sampling_step = 0
+    assert lib.yolat_proposals_ws_bytes(ctypes.byref(s)) == -1
+    s.sampling_step = 5
+    assert lib.yolat_proposals_count(ctypes.byref(s), None, 0, None, None) == -1
+    assert lib.yolat_proposals_fill(ctypes.byref(s), None, 0, None, None) == -1
+    assert lib.yolat_proposals_count(None, None, 0, None, None) == -1

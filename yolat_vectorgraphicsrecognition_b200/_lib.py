@@ -84,6 +84,9 @@ _SIGS = {
     'yolat_slice_graph_ints': (i64, [i64, i64]),
     'yolat_slice_graph': (C.c_int, [vp, i64, vp, i64, vp, i64, i64, vp, vp, vp, vp, vp]),
     'yolat_batch_offsets': (C.c_int, [vp, i64, vp, i64, vp, i64, vp]),
+    'yolat_proposals_ws_bytes': (i64, [vp]),
+    'yolat_proposals_count': (C.c_int, [vp, vp, i64, vp, vp]),
+    'yolat_proposals_fill': (C.c_int, [vp, vp, i64, vp, vp]),
     'yolat_adam_chunk': (C.c_int, []),
     'yolat_adam_step': (C.c_int, [vp, vp, i64, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_double, vp]),
