@@ -14,6 +14,7 @@ iteration order (`list(set(sub_clusters))`, `:557`).
 `do_mixup` (random augmentation, `:791-903`) is not part of this path.
 """
 import ctypes as C
+import gc
 
 import numpy as np
 import torch
@@ -152,33 +153,41 @@ def unpack_outputs(o, is_super_dtype):
     """The reference's 14-tuple (graph_dict3.py:787) from the flat outputs."""
     if o['edge_super'].shape[0] == 0 or o['edge'].shape[0] == 0:
         raise ValueError('need at least one array to concatenate')      # np.concatenate([]) at :772-773
-    b = o['labels'].shape[0]
-    sp, se, ss, sb = o['slice_pos'], o['slice_edge'], o['slice_super'], o['slice_bbox']
+    # the idxTree objects are the reference's return type (:730-750); python lists + dict literals keep their
+    # construction at ~1 us per proposal
+    sp, se, ss, sb = (o[k].tolist() for k in ('slice_pos', 'slice_edge', 'slice_super', 'slice_bbox'))
+    pos_r, edge_r, sup_r = list(zip(sp[:-1], sp[1:])), list(zip(se[:-1], se[1:])), list(zip(ss[:-1], ss[1:]))
+    new = idxTree.__new__
 
     def node(i):
-        t = idxTree()
-        t.value['idx_pos'] = (int(sp[i]), int(sp[i + 1]))
-        t.value['idx_edge'] = (int(se[i]), int(se[i + 1]))
-        t.value['idx_edge_super'] = (int(ss[i]), int(ss[i + 1]))
-        t.value['idx_bbox'] = int(sb[i])
+        t = new(idxTree)
+        t.children = []
+        t.value = {'idx_pos': pos_r[i], 'idx_edge': edge_r[i], 'idx_edge_super': sup_r[i], 'idx_bbox': sb[i]}
         return t
 
     roots = []
-    for first, count, root_i in o['cc_table'].tolist():               # :730-750
-        root = node(root_i)
-        root.children = [node(i) for i in range(first, first + count) if i != root_i]
-        roots.append(root)
+    gc_on = gc.isenabled()
+    gc.disable()                  # thousands of small containers: keep the cyclic collector from rescanning the heap
+    try:
+        for first, count, root_i in o['cc_table'].tolist():
+            root = node(root_i)
+            root.children = [node(i) for i in range(first, first + count) if i != root_i]
+            roots.append(root)
+    finally:
+        if gc_on:
+            gc.enable()
     pos = o['pos']
     return (pos, o['is_super'].reshape(-1, 1).astype(is_super_dtype), np.zeros((pos.shape[0], 1)), o['edge'],
             o['edge_super'], o['e_attr'], o['e_attr_super'], o['labels'].tolist(), o['bbox_idx'], o['bbox'],
             o['bbox_targets'], o['stat_feats'], o['has_obj'].tolist(), roots)
 
 
-def _sections_layout(arrays):
+def _sections_layout(sizes):
+    """256-byte aligned offsets of (name, nbytes) sections in one buffer."""
     offs, off = {}, 0
-    for name, a in arrays:
+    for name, nbytes in sizes:
         offs[name] = off
-        off += (a.nbytes + 255) // 256 * 256
+        off += (nbytes + 255) // 256 * 256
     return offs, max(off, 256)
 
 
@@ -196,7 +205,7 @@ def get_proposal(graph_dict, gt_bbox, gt_labels, bbox_sampling_step=5, n_classes
     with torch.cuda.device(device):
         # one pinned buffer, one H2D copy
         arrays = [(name, p[name]) for name in _SECTIONS]
-        offs, nbytes = _sections_layout(arrays)
+        offs, nbytes = _sections_layout([(name, a.nbytes) for name, a in arrays])
         host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
         hv = host.numpy()
         for name, a in arrays:
@@ -215,11 +224,11 @@ def get_proposal(graph_dict, gt_bbox, gt_labels, bbox_sampling_step=5, n_classes
         totals = totals_d.cpu().numpy()               # the one synchronisation: output sizes
         raise_for(totals)
         specs = output_specs(totals, s_in.A, s_in.As, s_in.ncc)
-        outs = [(name, np.empty(shape, dtype=dt)) for name, dt, shape in specs]
-        ooffs, onbytes = _sections_layout(outs)
+        nbytes_of = lambda dt, shape: int(np.prod(shape, dtype=np.int64)) * np.dtype(dt).itemsize
+        ooffs, onbytes = _sections_layout([(name, nbytes_of(dt, shape)) for name, dt, shape in specs])
         out_d = torch.empty(onbytes, dtype=torch.uint8, device=device)
         s_out = ProposalOut()
-        for name, _ in outs:
+        for name, _, _ in specs:
             setattr(s_out, name, out_d.data_ptr() + ooffs[name])
         _lib.check(lib.yolat_proposals_fill(C.byref(s_in), ws.data_ptr(), ws_bytes, C.byref(s_out), st), 'proposals_fill')
         out_h = torch.empty(onbytes, dtype=torch.uint8, pin_memory=True)
@@ -227,8 +236,8 @@ def get_proposal(graph_dict, gt_bbox, gt_labels, bbox_sampling_step=5, n_classes
         torch.cuda.current_stream().synchronize()
         ov = out_h.numpy()
         o = {}
-        for name, a in outs:
-            o[name] = ov[ooffs[name]:ooffs[name] + a.nbytes].view(a.dtype).reshape(a.shape).copy()
+        for name, dt, shape in specs:
+            o[name] = ov[ooffs[name]:ooffs[name] + nbytes_of(dt, shape)].view(dt).reshape(shape).copy()
     return unpack_outputs(o, p['is_super_dtype'])
 
 
