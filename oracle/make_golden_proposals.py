@@ -24,6 +24,8 @@ CASES = [
     (3, dict(n_cc=5, max_nodes=8, grid=3, with_control=False), 3, 17),
     (4, dict(n_cc=12, max_nodes=20, grid=12, parallel_edges=False), 5, 17),
     (5, dict(n_cc=3, max_nodes=40, grid=7), 7, 17),
+    (6, dict(n_cc=5, max_nodes=12, grid=5, jitter=0.8), 5, 17),                 # off the lattice: all coordinates distinct
+    (7, dict(n_cc=5, max_nodes=14, grid=5, jitter=0.3, dup_points=0.3), 5, 17), # nodes sitting on each other
 ]
 
 

@@ -294,11 +294,15 @@ def canonical_order(result):
 
 
 # ---- synthetic graph_dicts shaped like the Dataset's pickles (svg_parser.py output), for goldens and parity tests ----
-def synth_graph_dict(seed, n_cc=6, max_nodes=14, grid=6, with_control=True, n_gt_extra=3, parallel_edges=True):
+def synth_graph_dict(seed, n_cc=6, max_nodes=14, grid=6, with_control=True, n_gt_extra=3, parallel_edges=True,
+                     jitter=0.0, dup_points=0.0):
     """Components on disjoint patches of the unit square; node coordinates on a coarse lattice (repeated x / y values,
     as floor plans have), a spanning path plus random extra / parallel / self-loop edges per component, super edges,
     interleaved control points, 6-column edge attributes.  Ground truth: the box of every other component (IoU 1 ->
-    labelled), a shrunk box (IoS high, IoU low) and a few random boxes."""
+    labelled), a shrunk box (IoS high, IoU low) and a few random boxes.  `jitter` > 0 moves every node off the lattice
+    by a random fraction of a cell (arbitrary doubles, mostly distinct coordinate values, as parsed SVG has);
+    `dup_points` is the probability that a node sits exactly on an earlier node of its component.  Both default to off
+    and draw no random numbers then, so the committed goldens' inputs do not change."""
     rng = np.random.RandomState(seed)
     pos, is_control, is_super, cc, edges, supers = [], [], [], [], [], []
     gts, gt_labels = [], []
@@ -316,8 +320,14 @@ def synth_graph_dict(seed, n_cc=6, max_nodes=14, grid=6, with_control=True, n_gt
         for x, y in zip(px.tolist(), py.tolist()):
             if with_control and rng.rand() < 0.3:              # a control point in between (dropped by the o2n map)
                 pos.append([rng.rand(), rng.rand()]); is_control.append(1); is_super.append(0)
+            p = [ox + (0.05 + 0.9 * x / (grid - 1)) / cols, oy + (0.05 + 0.9 * y / (grid - 1)) / cols]
+            if jitter > 0:
+                p = [p[0] + jitter * (rng.rand() - 0.5) * 0.9 / (grid - 1) / cols,
+                     p[1] + jitter * (rng.rand() - 0.5) * 0.9 / (grid - 1) / cols]
+            if dup_points > 0 and len(ids) >= 3 and rng.rand() < dup_points:
+                p = list(pos[ids[int(rng.randint(0, len(ids)))]])
             ids.append(len(pos))
-            pos.append([ox + (0.05 + 0.9 * x / (grid - 1)) / cols, oy + (0.05 + 0.9 * y / (grid - 1)) / cols])
+            pos.append(p)
             is_control.append(0); is_super.append(int(rng.rand() < 0.1))
         order = rng.permutation(len(ids)).tolist()
         cc.append([ids[i] for i in order])

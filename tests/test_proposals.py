@@ -78,8 +78,9 @@ def test_oracle_matches_reference_goldens():
 def test_oracle_matches_live_reference():
     from oracle import make_golden_proposals as MG
     cls = MG.reference_class()
-    for seed, normalize in ((11, True), (12, False), (13, True)):
-        gd, gt_bbox, gt_labels = OP.synth_graph_dict(seed, n_cc=5, max_nodes=12, grid=5)
+    for seed, normalize, extra in ((11, True, {}), (12, False, {}), (13, True, {}), (14, True, dict(jitter=0.8)),
+                                   (15, True, dict(dup_points=0.3)), (16, False, dict(jitter=0.4, dup_points=0.2))):
+        gd, gt_bbox, gt_labels = OP.synth_graph_dict(seed, n_cc=5, max_nodes=12, grid=5, **extra)
         ref = OP.canonical_order(MG.run_reference(cls, gd, gt_bbox, gt_labels, 5, 17, normalize))
         got = OP.canonical_order(OP.get_proposal(gd, gt_bbox, gt_labels, 5, 17, normalize))
         assert_same_canon(got, ref, 'oracle vs live reference, seed %d' % seed)
@@ -159,6 +160,36 @@ def test_emulated_kernels_random_cases(emu):
             continue
         got = run_emu(emu, gd, gt_bbox, gt_labels, step, 17, normalize)
         assert_same_result(got, want, 'seed %d %r step %d' % (seed, kw, step))
+
+
+def test_emulated_kernels_off_lattice_duplicates_and_scale(emu):
+    """Arbitrary doubles (every coordinate value distinct), nodes sitting on each other, a larger sampling grid, and a
+    floor-plan-sized image with one large component."""
+    cases = [(200, dict(n_cc=5, max_nodes=16, grid=6, jitter=0.8), 5), (201, dict(n_cc=4, max_nodes=20, grid=5, dup_points=0.3), 5),
+             (202, dict(n_cc=3, max_nodes=30, grid=8, jitter=0.5, dup_points=0.2), 10),
+             (203, dict(n_cc=6, max_nodes=12, grid=4, jitter=1.0), 1), (204, dict(n_cc=2, max_nodes=60, grid=10, jitter=0.3), 16)]
+    for seed, kw, step in cases:
+        gd, gt_bbox, gt_labels = OP.synth_graph_dict(seed, **kw)
+        want = OP.get_proposal(gd, gt_bbox, gt_labels, step, 17, True)
+        assert_same_result(run_emu(emu, gd, gt_bbox, gt_labels, step, 17), want, 'seed %d %r step %d' % (seed, kw, step))
+    gd, gt_bbox, gt_labels = floorplan_scale_image()
+    assert_same_result(run_emu(emu, gd, gt_bbox, gt_labels, 5, 17), OP.get_proposal(gd, gt_bbox, gt_labels, 5, 17, True),
+                       'floor-plan scale')
+
+
+def floorplan_scale_image(n_cc=120):
+    """Hundreds of small components plus one large one (80 nodes on a 12 x 12 lattice) in a corner of the image."""
+    gd, gt_bbox, gt_labels = OP.synth_graph_dict(42, n_cc=n_cc, max_nodes=24, grid=9)
+    big, gtb, gtl = OP.synth_graph_dict(43, n_cc=1, max_nodes=80, grid=12)
+    n0 = gd['pos']['spatial'].shape[0]
+    gd['pos']['spatial'] = np.concatenate([gd['pos']['spatial'], big['pos']['spatial'] * 0.05 + 0.94])
+    gd['cc'].append([i + n0 for i in big['cc'][0]])
+    for k in ('shape', 'super'):
+        gd['edge'][k] = np.concatenate([gd['edge'][k], big['edge'][k] + n0])
+        gd['edge_attr'][k] = np.concatenate([gd['edge_attr'][k], big['edge_attr'][k]])
+    for k in ('is_super', 'is_control'):
+        gd['attr'][k] = np.concatenate([gd['attr'][k], big['attr'][k]])
+    return gd, np.concatenate([gt_bbox, gtb * 0.05 + 0.94]), np.concatenate([gt_labels, gtl])
 
 
 def _tiny():
@@ -259,6 +290,12 @@ def test_gpu_proposals_random_and_errors():
             continue
         got = P.get_proposal(gd, gt_bbox, gt_labels, step, 17, normalize)
         assert_same_result(got, want, 'seed %d %r step %d' % (seed, kw, step))
+    for seed, kw, step in [(200, dict(n_cc=5, max_nodes=16, grid=6, jitter=0.8), 5),
+                           (202, dict(n_cc=3, max_nodes=30, grid=8, jitter=0.5, dup_points=0.2), 10),
+                           (204, dict(n_cc=2, max_nodes=60, grid=10, jitter=0.3), 16)]:
+        gd, gt_bbox, gt_labels = OP.synth_graph_dict(seed, **kw)
+        assert_same_result(P.get_proposal(gd, gt_bbox, gt_labels, step, 17, True),
+                           OP.get_proposal(gd, gt_bbox, gt_labels, step, 17, True), 'seed %d' % seed)
     gd, gt, gl = _tiny()
     flat = dict(gd, pos={'spatial': np.array([[0.1, 0.1], [0.3, 0.1], [0.4, 0.1], [0.2, 0.1]])})
     with pytest.raises(ValueError, match='cannot compute length'):
@@ -271,18 +308,7 @@ def test_gpu_proposals_random_and_errors():
 def test_gpu_proposals_floorplan_scale():
     """A floor-plan-sized image (hundreds of components, one of them large): against the oracle, and run twice
     (bit-identical outputs: the atomics only order scratch lists that are sorted afterwards)."""
-    gd, gt_bbox, gt_labels = OP.synth_graph_dict(42, n_cc=120, max_nodes=24, grid=9)
-    big, gtb, gtl = OP.synth_graph_dict(43, n_cc=1, max_nodes=80, grid=12)
-    n0 = gd['pos']['spatial'].shape[0]
-    gd['pos']['spatial'] = np.concatenate([gd['pos']['spatial'], big['pos']['spatial'] * 0.05 + 0.94])
-    gd['cc'].append([i + n0 for i in big['cc'][0]])
-    for k in ('shape', 'super'):
-        gd['edge'][k] = np.concatenate([gd['edge'][k], big['edge'][k] + n0])
-        gd['edge_attr'][k] = np.concatenate([gd['edge_attr'][k], big['edge_attr'][k]])
-    for k in ('is_super', 'is_control'):
-        gd['attr'][k] = np.concatenate([gd['attr'][k], big['attr'][k]])
-    gt_bbox = np.concatenate([gt_bbox, gtb * 0.05 + 0.94])
-    gt_labels = np.concatenate([gt_labels, gtl])
+    gd, gt_bbox, gt_labels = floorplan_scale_image()
     a = P.get_proposal(gd, gt_bbox, gt_labels, 5, 17, True)
     b = P.get_proposal(gd, gt_bbox, gt_labels, 5, 17, True)
     for x, y in zip(a[:13], b[:13]):
