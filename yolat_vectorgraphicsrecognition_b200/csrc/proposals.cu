@@ -156,47 +156,56 @@ __device__ T block_sum(T v, T* sh) {
   __syncthreads();
   return r;
 }
-template <typename T>
-__device__ T block_max(T v, T* sh) {
-  const int tid = threadIdx.x;
-  sh[tid] = v;
-  __syncthreads();
-  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
-    if (tid < s && sh[tid + s] > sh[tid]) sh[tid] = sh[tid + s];
-    __syncthreads();
-  }
-  const T r = sh[0];
-  __syncthreads();
-  return r;
-}
-template <typename T>
-__device__ T block_min(T v, T* sh) {
-  const int tid = threadIdx.x;
-  sh[tid] = v;
-  __syncthreads();
-  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
-    if (tid < s && sh[tid + s] < sh[tid]) sh[tid] = sh[tid + s];
-    __syncthreads();
-  }
-  const T r = sh[0];
-  __syncthreads();
-  return r;
-}
 // exclusive scan of one value per thread; *total = sum over the block
-__device__ int block_excl_scan(int v, int* sh, int* total) {
+template <typename T>
+__device__ T block_excl_scan(T v, T* sh, T* total) {
   const int tid = threadIdx.x;
   sh[tid] = v;
   __syncthreads();
   for (int off = 1; off < (int)blockDim.x; off <<= 1) {
-    const int t = tid >= off ? sh[tid - off] : 0;
+    const T t = tid >= off ? sh[tid - off] : 0;
     __syncthreads();
     sh[tid] += t;
     __syncthreads();
   }
-  const int incl = sh[tid];
+  const T incl = sh[tid];
   *total = sh[blockDim.x - 1];
   __syncthreads();
   return incl - v;
+}
+
+// One reduction tree for everything a candidate needs at once: four integer sums, two double sums, a maximum, a
+// minimum and an arg-max (largest key; the smallest arg among equal keys = numpy's first maximum).
+struct Acc {
+  long long l[4];
+  double s[2];
+  double mx, mn, key;
+  long long arg;
+};
+__device__ inline void acc_init(Acc& a) {
+  for (int i = 0; i < 4; ++i) a.l[i] = 0;
+  a.s[0] = a.s[1] = 0.0;
+  a.mx = -INFINITY; a.mn = INFINITY; a.key = -INFINITY;
+  a.arg = 0x7fffffffffffffffll;
+}
+__device__ inline void acc_merge(Acc& a, const Acc& b) {
+  for (int i = 0; i < 4; ++i) a.l[i] += b.l[i];
+  a.s[0] += b.s[0]; a.s[1] += b.s[1];
+  if (b.mx > a.mx) a.mx = b.mx;
+  if (b.mn < a.mn) a.mn = b.mn;
+  if (b.key > a.key || (b.key == a.key && b.arg < a.arg)) { a.key = b.key; a.arg = b.arg; }
+}
+__device__ Acc block_reduce(const Acc& v, Acc* sh) {
+  const int tid = threadIdx.x;
+  sh[tid] = v;
+  __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (tid < s) acc_merge(sh[tid], sh[tid + s]);
+    __syncthreads();
+  }
+  const Acc r = sh[0];
+  __syncthreads();
+  return r;
 }
 
 __device__ inline void raise_err(int64_t* totals, unsigned long long bit, int cc) {
@@ -207,22 +216,26 @@ __device__ inline void raise_err(int64_t* totals, unsigned long long bit, int cc
 // ---- (1) control-point compaction: o2n[i] = number of non-control nodes before i (graph_dict3.py:325-330) ---------
 __global__ void __launch_bounds__(kThreads) k_prop_o2n(In in, Ws w) {
   __shared__ int sh[kThreads];
+  constexpr int kPer = 8;                                  // consecutive nodes per thread and chunk
   const int tid = threadIdx.x, bd = blockDim.x;
   int carry = 0;
-  for (int64_t base = 0; base < in.n_all; base += bd) {
-    const int64_t i = base + tid;
-    const int keep = (i < in.n_all && in.is_control[i] == 0) ? 1 : 0;
+  for (int64_t base = 0; base < in.n_all; base += (int64_t)bd * kPer) {
+    const int64_t i0 = base + (int64_t)tid * kPer;
+    int mine = 0;
+    for (int t = 0; t < kPer; ++t) mine += (i0 + t < in.n_all && in.is_control[i0 + t] == 0) ? 1 : 0;
     int tot;
-    const int ex = block_excl_scan(keep, sh, &tot);
-    if (i < in.n_all) {
-      if (keep) {
-        const int q = carry + ex;
+    int q = carry + block_excl_scan<int>(mine, sh, &tot);
+    for (int t = 0; t < kPer; ++t) {
+      const int64_t i = i0 + t;
+      if (i >= in.n_all) break;
+      if (in.is_control[i] == 0) {
         w.o2n[i] = q;
         w.pos[2 * q] = in.pos[2 * i];
         w.pos[2 * q + 1] = in.pos[2 * i + 1];
         w.issup[q] = in.is_super[i];
         w.node_cc[q] = -1;
         w.node_loc[q] = 0;
+        ++q;
       } else {
         w.o2n[i] = -1;
       }
@@ -351,7 +364,7 @@ __global__ void __launch_bounds__(kThreads) k_prop_edge_scan(In in, Ws w) {
       const int64_t i = base + tid;
       const int v = i < in.ncc ? cnt[i] : 0;
       int tot;
-      const int ex = block_excl_scan(v, sh, &tot);
+      const int ex = block_excl_scan<int>(v, sh, &tot);
       if (i < in.ncc) { ptr[i] = carry + ex; cur[i] = 0; }
       carry += tot;
     }
@@ -452,13 +465,9 @@ __device__ inline bool gt_touches(const double* ccb, const double* g) {
   return ix2 > ix1 && iy2 > iy1;
 }
 
-struct Angles { long long cnt, more, less, eq; double sum, mx, mn; };
-
 // dot products of every pair of distinct neighbours of every anchor inside the box (graph_dict3.py:646-669).
-// pass 0 accumulates counts / sum / extrema, pass 1 the squared deviations from `mean` (returned in sum).
-__device__ Angles cc_angles(const Ws& w, int64_t nb, int nc, int d0, int nd, const Box& box, int pass, double mean) {
-  Angles a;
-  a.cnt = a.more = a.less = a.eq = 0; a.sum = 0.0; a.mx = -INFINITY; a.mn = INFINITY;
+// pass 0: l[0..3] = number of angles / obtuse / acute / right, s[0] = sum, mx / mn; pass 1: s[0] += (dot - mean)^2
+__device__ void cc_angles(const Ws& w, int64_t nb, int nc, int d0, int nd, const Box& box, int pass, double mean, Acc& a) {
   const int32_t* da = w.da + d0;
   const int32_t* db = w.db + d0;
   for (int r = threadIdx.x; r < nc; r += blockDim.x) {
@@ -480,27 +489,25 @@ __device__ Angles cc_angles(const Ws& w, int64_t nb, int nc, int d0, int nd, con
         const double v1x = w.pos[2 * w.cs[nb + db[j]]] - ax, v1y = w.pos[2 * w.cs[nb + db[j]] + 1] - ay;
         const double dot = v0x * v1x + v0y * v1y;
         if (pass == 0) {
-          if (dot <= -1e-2) ++a.more;
-          else if (dot >= 1e-2) ++a.less;
-          else if (fabs(dot) < 1e-2) ++a.eq;
-          ++a.cnt;
-          a.sum += dot;
+          if (dot <= -1e-2) ++a.l[1];
+          else if (dot >= 1e-2) ++a.l[2];
+          else if (fabs(dot) < 1e-2) ++a.l[3];
+          ++a.l[0];
+          a.s[0] += dot;
           if (dot > a.mx) a.mx = dot;
           if (dot < a.mn) a.mn = dot;
         } else {
           const double d = dot - mean;
-          a.sum += d * d;
+          a.s[0] += d * d;
         }
       }
     }
   }
-  return a;
 }
 
 // ---- (2d, 3) one CTA per component: sort, window walk, de-duplication, evaluation ---------------------------------
 __global__ void __launch_bounds__(kThreads) k_prop_cc_main(In in, Ws w, int wmax) {
-  __shared__ double sh_d[kThreads];
-  __shared__ long long sh_l[kThreads];
+  __shared__ Acc sh_acc[kThreads];
   __shared__ int sh_i[kThreads];
   __shared__ double s_xg[kMaxLines], s_yg[kMaxLines];
   __shared__ int s_lbx[kMaxLines], s_ubx[kMaxLines], s_lby[kMaxLines], s_uby[kMaxLines];
@@ -656,7 +663,7 @@ __global__ void __launch_bounds__(kThreads) k_prop_cc_main(In in, Ws w, int wmax
       }
     }
     int tot;
-    const int ex = block_excl_scan(keep, sh_i, &tot);
+    const int ex = block_excl_scan<int>(keep, sh_i, &tot);
     if (keep) {
       const int k = ncand + ex;
       const int32_t* t = w.tight + 4 * (slot0 + wi);
@@ -677,7 +684,7 @@ __global__ void __launch_bounds__(kThreads) k_prop_cc_main(In in, Ws w, int wmax
     return;
   }
 
-  // -- every candidate, all threads together
+  // -- every candidate, all threads together: three reductions per candidate
   long long tn = 0, te = 0, ts = 0, tb = 0;
   int root = -1;
   double root_area = 0.0;
@@ -686,67 +693,59 @@ __global__ void __launch_bounds__(kThreads) k_prop_cc_main(In in, Ws w, int wmax
     const int64_t slot = slot0 + k;
     const int32_t* q = w.cbox + 4 * slot;
     const Box box = {q[0], q[1], q[2], q[3]};
-    if (tid == 0) w.csurv[slot] = 0;
-    // induced shape edges (both ends inside, no self loop) and the sum of their distance attribute
-    long long cnt = 0;
-    double dsum = 0.0;
-    for (int j = tid; j < m; j += bd) {
-      const int a = w.ea[e0 + j], b = w.eb[e0 + j];
-      if (a != b && inside(w, nb, a, box) && inside(w, nb, b, box)) {
-        ++cnt;
-        dsum += in.e_attr[(int64_t)w.esort[e0 + j] * in.A + acol];
-      }
-    }
-    const long long mk = block_sum<long long>(cnt, sh_l);
-    if (mk == 0) continue;                                 // :594-596
-    dsum = block_sum<double>(dsum, sh_d);
-    cnt = 0;
-    for (int j = tid; j < ms; j += bd) {
-      const int a = w.sa[s0 + j], b = w.sb[s0 + j];
-      if (a != b && inside(w, nb, a, box) && inside(w, nb, b, box)) ++cnt;
-    }
-    const long long msk = block_sum<long long>(cnt, sh_l);
     const double pb[4] = {xv[box.x0], yv[box.y0], xv[box.x1], yv[box.y1]};
     const double width = pb[2] - pb[0], height = pb[3] - pb[1];
-    if (width < 1e-4 || height < 1e-4) continue;           // :616-617
-
-    // label by the best-overlapping touching ground-truth box (:619-637): first maximum of IoU
-    double best = -INFINITY;
-    long long best_g = 0x7fffffffffffffffll;
+    if (tid == 0) w.csurv[slot] = 0;
+    // (i) induced shape / super edges (both ends inside, no self loop), the sum of the shape edges' distance attribute,
+    //     and the best-overlapping touching ground-truth box (:619-637: first maximum of IoU)
+    Acc a;
+    acc_init(a);
+    for (int j = tid; j < m; j += bd) {
+      const int ja = w.ea[e0 + j], jb = w.eb[e0 + j];
+      if (ja != jb && inside(w, nb, ja, box) && inside(w, nb, jb, box)) {
+        ++a.l[0];
+        a.s[0] += in.e_attr[(int64_t)w.esort[e0 + j] * in.A + acol];
+      }
+    }
+    for (int j = tid; j < ms; j += bd) {
+      const int ja = w.sa[s0 + j], jb = w.sb[s0 + j];
+      if (ja != jb && inside(w, nb, ja, box) && inside(w, nb, jb, box)) ++a.l[1];
+    }
     for (int64_t g = tid; g < in.G; g += bd) {
       const double* gb = in.gt_bbox + 4 * g;
       if (!gt_touches(ccb, gb)) continue;
       const double v = iou_ios(pb, gb).iou;
-      if (v > best) { best = v; best_g = g; }
+      if (v > a.key) { a.key = v; a.arg = g; }
     }
-    const double best_all = block_max<double>(best, sh_d);
-    long long gsel = block_min<long long>(best == best_all ? best_g : 0x7fffffffffffffffll, sh_l);
+    a = block_reduce(a, sh_acc);
+    const long long mk = a.l[0], msk = a.l[1];
+    if (mk == 0) continue;                                 // :594-596
+    if (width < 1e-4 || height < 1e-4) continue;           // :616-617
+    const double dmean = a.s[0] / (double)mk;
+    long long gsel = a.arg;
     if (gsel >= in.G) gsel = 0;                            // only with NaN boxes (np.argmax would pick the first NaN)
     const Iou sel = iou_ios(pb, in.gt_bbox + 4 * gsel);
 
-    // angles (:640-675) and the distance statistics (:686-687)
-    Angles a = cc_angles(w, nb, nc, d0, nd, box, 0, 0.0);
-    const long long acnt = block_sum<long long>(a.cnt, sh_l);
+    // (ii) angles (:640-675)
+    acc_init(a);
+    cc_angles(w, nb, nc, d0, nd, box, 0, 0.0, a);
+    a = block_reduce(a, sh_acc);
+    const long long acnt = a.l[0], n_more = a.l[1], n_less = a.l[2], n_eq = a.l[3];
     if (acnt == 0) continue;                               // :674-675
-    const long long n_more = block_sum<long long>(a.more, sh_l);
-    const long long n_less = block_sum<long long>(a.less, sh_l);
-    const long long n_eq = block_sum<long long>(a.eq, sh_l);
-    const double asum = block_sum<double>(a.sum, sh_d);
-    const double amax = block_max<double>(a.mx, sh_d);
-    const double amin = block_min<double>(a.mn, sh_d);
-    const double amean = asum / (double)acnt;
-    a = cc_angles(w, nb, nc, d0, nd, box, 1, amean);
-    const double avar = block_sum<double>(a.sum, sh_d) / (double)acnt;
-    const double dmean = dsum / (double)mk;
-    double dss = 0.0;
+    const double amean = a.s[0] / (double)acnt, amax = a.mx, amin = a.mn;
+
+    // (iii) squared deviations of the angles and of the distance attribute (np.std: two-pass, population)
+    acc_init(a);
+    cc_angles(w, nb, nc, d0, nd, box, 1, amean, a);
     for (int j = tid; j < m; j += bd) {
       const int ja = w.ea[e0 + j], jb = w.eb[e0 + j];
       if (ja != jb && inside(w, nb, ja, box) && inside(w, nb, jb, box)) {
         const double d = in.e_attr[(int64_t)w.esort[e0 + j] * in.A + acol] - dmean;
-        dss += d * d;
+        a.s[1] += d * d;
       }
     }
-    const double dvar = block_sum<double>(dss, sh_d) / (double)mk;
+    a = block_reduce(a, sh_acc);
+    const double avar = a.s[0] / (double)acnt, dvar = a.s[1] / (double)mk;
 
     if (tid == 0) {
       const int nk = w.ccnt[slot];
@@ -776,22 +775,18 @@ __global__ void __launch_bounds__(kThreads) k_prop_cc_main(In in, Ws w, int wmax
 // ---- (4a) offsets of every component's block of proposals ---------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_prop_cc_scan(In in, Ws w) {
   __shared__ long long sh[kThreads];
-  const int tid = threadIdx.x;
-  // four independent scans over ncc entries; components are few (hundreds): one thread per quantity
-  for (int q = tid; q < 4; q += blockDim.x) {
-    long long run = 0;
-    for (int64_t c = 0; c < in.ncc; ++c) {
-      w.cc_off[4 * c + q] = run;
-      run += w.cc_tot[4 * c + q];
+  const int tid = threadIdx.x, bd = blockDim.x;
+  for (int q = 0; q < 4; ++q) {                            // nodes, shape edges, super edges, proposals
+    long long carry = 0;
+    for (int64_t base = 0; base < in.ncc; base += bd) {
+      const int64_t c = base + tid;
+      const long long v = c < in.ncc ? (long long)w.cc_tot[4 * c + q] : 0;
+      long long tot;
+      const long long ex = block_excl_scan<long long>(v, sh, &tot);
+      if (c < in.ncc) w.cc_off[4 * c + q] = carry + ex;
+      carry += tot;
     }
-    sh[q] = run;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    w.totals[YOLAT_PROP_T_NODES] = sh[0];
-    w.totals[YOLAT_PROP_T_EDGES] = sh[1];
-    w.totals[YOLAT_PROP_T_SUPER] = sh[2];
-    w.totals[YOLAT_PROP_T_BOXES] = sh[3];
+    if (tid == 0) w.totals[YOLAT_PROP_T_NODES + q] = carry;   // T_NODES, T_EDGES, T_SUPER, T_BOXES are consecutive
   }
 }
 
@@ -809,7 +804,7 @@ __device__ void fill_edges(const Ws& w, int64_t nb, const Box& box, int m, const
       keep = (a != b && inside(w, nb, a, box) && inside(w, nb, b, box)) ? 1 : 0;
     }
     int tot;
-    const int ex = block_excl_scan(keep, sh, &tot);
+    const int ex = block_excl_scan<int>(keep, sh, &tot);
     if (keep) {
       const int64_t o = edge_off + done + ex;
       edge_out[2 * o] = node_off + w.lrank[nb + a];
@@ -854,7 +849,7 @@ __global__ void __launch_bounds__(kThreads) k_prop_fill(In in, Ws w, Out out, in
       const int r = base + tid;
       const int keep = (r < nc && inside(w, nb, r, box)) ? 1 : 0;
       int tot;
-      const int ex = block_excl_scan(keep, sh, &tot);
+      const int ex = block_excl_scan<int>(keep, sh, &tot);
       if (keep) {
         const int lr = done + ex;
         w.lrank[nb + r] = lr;
