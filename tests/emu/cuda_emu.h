@@ -2,7 +2,8 @@
 // CPU suite can compile that very file with g++ (-x c++ -DYOLAT_HOST_EMU) and check its logic against the oracle
 // without a GPU.  "Device" pointers are host pointers, CTAs run one after another.
 //   default             one thread per CTA (blockDim.x == 1), __syncthreads() is a no-op: checks the logic.
-//   -DEMU_THREADS=N     N host threads per CTA (N a power of two), __syncthreads() is a pthread barrier, atomics are
+//   -DEMU_THREADS=N     N host threads per CTA (N a power of two), __syncthreads() is a pthread barrier, __syncwarp() a
+//                       barrier of the thread's group of min(N, 32) consecutive threads, atomics are
 //                       real atomics: checks the same logic under real concurrency, and -- built with
 //                       -fsanitize=thread -- reports shared / global accesses that no barrier orders (missing
 //                       __syncthreads()).
@@ -37,6 +38,7 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int,
 #if EMU_THREADS == 1
 static emu_dim3 threadIdx = {0, 0, 0};
 static inline void __syncthreads() {}
+static inline void __syncwarp() {}
 static inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
 static inline int atomicExch(int* p, int v) { const int o = *p; *p = v; return o; }
 static inline unsigned long long atomicOr(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o | v; return o; }
@@ -54,8 +56,10 @@ static inline unsigned long long atomicMin(unsigned long long* p, unsigned long 
 #include <thread>
 #include <vector>
 static thread_local emu_dim3 threadIdx = {0, 0, 0};
-static pthread_barrier_t emu_barrier;
+#define EMU_GROUP (EMU_THREADS < 32 ? EMU_THREADS : 32)        /* threads per "warp" */
+static pthread_barrier_t emu_barrier, emu_group_barrier[EMU_THREADS / EMU_GROUP];
 static inline void __syncthreads() { pthread_barrier_wait(&emu_barrier); }
+static inline void __syncwarp() { pthread_barrier_wait(&emu_group_barrier[threadIdx.x / EMU_GROUP]); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicOr(unsigned long long* p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
@@ -71,11 +75,13 @@ static inline unsigned long long atomicMin(unsigned long long* p, unsigned long 
     for (unsigned _b = 0; _b < (unsigned)(grid); ++_b) {                                 \
       blockIdx.x = _b;                                                                   \
       pthread_barrier_init(&emu_barrier, nullptr, EMU_THREADS);                          \
+      for (auto& _gb : emu_group_barrier) pthread_barrier_init(&_gb, nullptr, EMU_GROUP); \
       std::vector<std::thread> _ts;                                                      \
       for (unsigned _t = 0; _t < EMU_THREADS; ++_t)                                      \
         _ts.emplace_back([&, _t] { threadIdx.x = _t; kern(__VA_ARGS__); });              \
       for (auto& _th : _ts) _th.join();                                                  \
       pthread_barrier_destroy(&emu_barrier);                                             \
+      for (auto& _gb : emu_group_barrier) pthread_barrier_destroy(&_gb);                 \
     }                                                                                    \
   } while (0)
 #endif

@@ -105,9 +105,10 @@ def bind_emu(so):
     return lib
 
 
-@pytest.fixture(scope='module', params=[1, 8], ids=['1thread', '8threads'])
+@pytest.fixture(scope='module', params=[1, 8, 64], ids=['1thread', '8threads', '64threads'])
 def emu(request, tmp_path_factory):
-    """csrc/proposals.cu compiled for the host: one thread per CTA, and 8 real threads per CTA with barriers."""
+    """csrc/proposals.cu compiled for the host: one thread per CTA; 8 real threads per CTA (one group); 64 real threads
+    per CTA (two "warps" of 32, each candidate handled by one of them) with CTA and group barriers."""
     if shutil.which('g++') is None:
         pytest.skip('g++ not available')
     so = str(tmp_path_factory.mktemp('emu') / ('libprop_emu%d.so' % request.param))
@@ -233,14 +234,14 @@ def test_error_conditions_match_reference(emu):
 
 
 def test_emulated_kernels_are_race_free(tmp_path):
-    """ThreadSanitizer over the 4-threads-per-CTA emulation: every shared / global access of a CTA must be ordered by a
-    barrier (a missing __syncthreads() is reported as a data race)."""
+    """ThreadSanitizer over the 64-threads-per-CTA emulation (two groups of 32): every shared / global access of a CTA
+    must be ordered by a CTA or group barrier (a missing __syncthreads() / __syncwarp() is reported as a data race)."""
     if shutil.which('g++') is None:
         pytest.skip('g++ not available')
     tsan = subprocess.run(['g++', '-print-file-name=libtsan.so'], capture_output=True, text=True).stdout.strip()
     if not os.path.isabs(tsan) or not os.path.exists(tsan):
         pytest.skip('libtsan not available')
-    so = build_emu(str(tmp_path / 'libprop_tsan.so'), 4, ['-fsanitize=thread', '-O1'])
+    so = build_emu(str(tmp_path / 'libprop_tsan.so'), 64, ['-fsanitize=thread', '-O1'])
     env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS='report_signal_unsafe=0 exitcode=66')
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'emu', 'tsan_driver.py'), so, '0', '1'], env=env,

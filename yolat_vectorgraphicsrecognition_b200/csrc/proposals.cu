@@ -28,9 +28,14 @@
 // that decides something (grid lines, box, IoU / IoS thresholds, dot-product classes) bit for bit (-fmad=false),
 // means / standard deviations up to summation order.
 //
+// Candidates are independent, so k_prop_cc_main / k_prop_fill give each one to a GROUP (a warp: 32 consecutive threads,
+// reductions and scans through shared memory ordered by __syncwarp()); CTA barriers only separate the per-component
+// phases.  (Profile of the first version, one CTA-wide loop over candidates: 71 % of the warp stalls at CTA barriers
+// with one warp's worth of work per candidate -- profiles/r2_prop_cc_main_stalls.txt.)
+//
 // Every kernel is written for any power-of-two blockDim: the CPU suite compiles this very file with
-// -DYOLAT_HOST_EMU against tests/emu/cuda_emu.h (one thread per CTA, CTAs in sequence) to check the logic without a
-// GPU; that build is test infrastructure and is never part of libyolat_b200.so.
+// -DYOLAT_HOST_EMU against tests/emu/cuda_emu.h (1 / 8 / 64 host threads per CTA, CTAs in sequence) to check the
+// logic and the barriers without a GPU; that build is test infrastructure and is never part of libyolat_b200.so.
 #ifdef YOLAT_HOST_EMU
 #include "cuda_emu.h"
 #else
@@ -44,6 +49,7 @@ namespace prop {
 
 constexpr int kThreads = 256;
 constexpr int kMaxLines = 64;               // grid lines per axis: bbox_sampling_step + 2 at most
+constexpr int kGroup = 32;                  // threads that share one candidate (a warp)
 constexpr int kStats = 13;                  // stat_feats columns (graph_dict3.py:690-691)
 constexpr int kLocBits = 20, kIdBits = 24;  // sort keys: (lo:20 | hi:20 | id:24)
 constexpr unsigned long long kLocMask = (1ull << kLocBits) - 1, kIdMask = (1ull << kIdBits) - 1;
@@ -60,7 +66,7 @@ struct Ws {
   int32_t *elist, *esort, *ea, *eb, *slist, *ssort, *sa, *sb;
   unsigned long long *key_e, *key_s, *key_d;
   int32_t *da, *db, *dcnt;
-  int32_t *win, *tight, *wcnt, *cbox, *ccnt, *cm, *cms, *csurv, *clabel, *chas, *cgt;
+  int32_t *win, *tight, *wcnt, *cbox, *ccnt, *cm, *cms, *csurv, *clabel, *chas, *cgt, *coff;
   double* cstats;
   int32_t *ncand, *cc_root;
   int64_t *cc_tot, *cc_off;
@@ -96,7 +102,7 @@ static int64_t carve(const In& in, char* base, Ws* w) {
   t.yi = (int32_t*)take(4 * ct);
   t.t0 = (int32_t*)take(4 * ct);
   t.t1 = (int32_t*)take(4 * ct);
-  t.lrank = (int32_t*)take(4 * ct);
+  t.lrank = (int32_t*)take(4 * ct * (kThreads / kGroup));     // one copy per group of k_prop_fill
   t.xv = (double*)take(8 * ct);
   t.yv = (double*)take(8 * ct);
   t.nxy = (int32_t*)take(8 * ncc);
@@ -133,6 +139,7 @@ static int64_t carve(const In& in, char* base, Ws* w) {
   t.clabel = (int32_t*)take(4 * slots);
   t.chas = (int32_t*)take(4 * slots);
   t.cgt = (int32_t*)take(4 * slots);
+  t.coff = (int32_t*)take(16 * slots);
   t.cstats = (double*)take(8 * kStats * slots);
   t.ncand = (int32_t*)take(4 * ncc);
   t.cc_root = (int32_t*)take(4 * ncc);
@@ -206,6 +213,63 @@ __device__ Acc block_reduce(const Acc& v, Acc* sh) {
   const Acc r = sh[0];
   __syncthreads();
   return r;
+}
+
+// ---- group-level helpers: a group = min(kGroup, blockDim) consecutive threads (one warp on the device); `sh` points at
+// the group's own segment of a shared array, __syncwarp() orders the group's shared-memory accesses
+struct Group { int size, lane, id, count; };
+__device__ inline Group this_group() {
+  Group g;
+  g.size = (int)blockDim.x < kGroup ? (int)blockDim.x : kGroup;
+  g.lane = (int)threadIdx.x % g.size;
+  g.id = (int)threadIdx.x / g.size;
+  g.count = (int)blockDim.x / g.size;
+  return g;
+}
+__device__ Acc group_reduce(const Acc& v, Acc* sh, const Group& g) {
+  sh[g.lane] = v;
+  __syncwarp();
+  for (int s = g.size >> 1; s > 0; s >>= 1) {
+    if (g.lane < s) acc_merge(sh[g.lane], sh[g.lane + s]);
+    __syncwarp();
+  }
+  const Acc r = sh[0];
+  __syncwarp();
+  return r;
+}
+__device__ int group_excl_scan(int v, int* sh, const Group& g, int* total) {
+  sh[g.lane] = v;
+  __syncwarp();
+  for (int off = 1; off < g.size; off <<= 1) {
+    const int t = g.lane >= off ? sh[g.lane - off] : 0;
+    __syncwarp();
+    sh[g.lane] += t;
+    __syncwarp();
+  }
+  const int incl = sh[g.lane];
+  *total = sh[g.size - 1];
+  __syncwarp();
+  return incl - v;
+}
+// four running sums scanned together (nodes, shape edges, super edges, proposals); plain aggregate (shared arrays of it)
+struct I4 { int v[4]; };
+__device__ inline I4 i4_zero() { I4 r; r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0; return r; }
+__device__ I4 block_excl_scan_i4(const I4& v, I4* sh, I4* total) {
+  const int tid = threadIdx.x;
+  sh[tid] = v;
+  __syncthreads();
+  for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+    I4 t = i4_zero();
+    if (tid >= off) t = sh[tid - off];
+    __syncthreads();
+    for (int i = 0; i < 4; ++i) sh[tid].v[i] += t.v[i];
+    __syncthreads();
+  }
+  I4 ex = sh[tid];
+  for (int i = 0; i < 4; ++i) ex.v[i] -= v.v[i];
+  *total = sh[blockDim.x - 1];
+  __syncthreads();
+  return ex;
 }
 
 __device__ inline void raise_err(int64_t* totals, unsigned long long bit, int cc) {
@@ -467,10 +531,11 @@ __device__ inline bool gt_touches(const double* ccb, const double* g) {
 
 // dot products of every pair of distinct neighbours of every anchor inside the box (graph_dict3.py:646-669).
 // pass 0: l[0..3] = number of angles / obtuse / acute / right, s[0] = sum, mx / mn; pass 1: s[0] += (dot - mean)^2
-__device__ void cc_angles(const Ws& w, int64_t nb, int nc, int d0, int nd, const Box& box, int pass, double mean, Acc& a) {
+__device__ void cc_angles(const Ws& w, int64_t nb, int nc, int d0, int nd, const Box& box, int pass, double mean, Acc& a,
+                          const Group& g) {
   const int32_t* da = w.da + d0;
   const int32_t* db = w.db + d0;
-  for (int r = threadIdx.x; r < nc; r += blockDim.x) {
+  for (int r = g.lane; r < nc; r += g.size) {
     if (!inside(w, nb, r, box)) continue;
     int lo = 0, hi = nd;                                   // first directed entry of anchor r
     while (lo < hi) {
@@ -508,6 +573,7 @@ __device__ void cc_angles(const Ws& w, int64_t nb, int nc, int d0, int nd, const
 // ---- (2d, 3) one CTA per component: sort, window walk, de-duplication, evaluation ---------------------------------
 __global__ void __launch_bounds__(kThreads) k_prop_cc_main(In in, Ws w, int wmax) {
   __shared__ Acc sh_acc[kThreads];
+  __shared__ I4 sh_i4[kThreads];
   __shared__ int sh_i[kThreads];
   __shared__ double s_xg[kMaxLines], s_yg[kMaxLines];
   __shared__ int s_lbx[kMaxLines], s_ubx[kMaxLines], s_lby[kMaxLines], s_uby[kMaxLines];
@@ -684,40 +750,39 @@ __global__ void __launch_bounds__(kThreads) k_prop_cc_main(In in, Ws w, int wmax
     return;
   }
 
-  // -- every candidate, all threads together: three reductions per candidate
-  long long tn = 0, te = 0, ts = 0, tb = 0;
-  int root = -1;
-  double root_area = 0.0;
+  // -- every candidate: one group each, three group reductions per candidate, no CTA barrier inside the loop
+  const Group g = this_group();
+  Acc* gsh = sh_acc + g.id * g.size;
   const int acol = in.A - 1;
-  for (int k = 0; k < ncand; ++k) {
+  for (int k = g.id; k < ncand; k += g.count) {
     const int64_t slot = slot0 + k;
     const int32_t* q = w.cbox + 4 * slot;
     const Box box = {q[0], q[1], q[2], q[3]};
     const double pb[4] = {xv[box.x0], yv[box.y0], xv[box.x1], yv[box.y1]};
     const double width = pb[2] - pb[0], height = pb[3] - pb[1];
-    if (tid == 0) w.csurv[slot] = 0;
+    if (g.lane == 0) w.csurv[slot] = 0;
     // (i) induced shape / super edges (both ends inside, no self loop), the sum of the shape edges' distance attribute,
     //     and the best-overlapping touching ground-truth box (:619-637: first maximum of IoU)
     Acc a;
     acc_init(a);
-    for (int j = tid; j < m; j += bd) {
+    for (int j = g.lane; j < m; j += g.size) {
       const int ja = w.ea[e0 + j], jb = w.eb[e0 + j];
       if (ja != jb && inside(w, nb, ja, box) && inside(w, nb, jb, box)) {
         ++a.l[0];
         a.s[0] += in.e_attr[(int64_t)w.esort[e0 + j] * in.A + acol];
       }
     }
-    for (int j = tid; j < ms; j += bd) {
+    for (int j = g.lane; j < ms; j += g.size) {
       const int ja = w.sa[s0 + j], jb = w.sb[s0 + j];
       if (ja != jb && inside(w, nb, ja, box) && inside(w, nb, jb, box)) ++a.l[1];
     }
-    for (int64_t g = tid; g < in.G; g += bd) {
-      const double* gb = in.gt_bbox + 4 * g;
+    for (int64_t t = g.lane; t < in.G; t += g.size) {
+      const double* gb = in.gt_bbox + 4 * t;
       if (!gt_touches(ccb, gb)) continue;
       const double v = iou_ios(pb, gb).iou;
-      if (v > a.key) { a.key = v; a.arg = g; }
+      if (v > a.key) { a.key = v; a.arg = t; }
     }
-    a = block_reduce(a, sh_acc);
+    a = group_reduce(a, gsh, g);
     const long long mk = a.l[0], msk = a.l[1];
     if (mk == 0) continue;                                 // :594-596
     if (width < 1e-4 || height < 1e-4) continue;           // :616-617
@@ -728,27 +793,26 @@ __global__ void __launch_bounds__(kThreads) k_prop_cc_main(In in, Ws w, int wmax
 
     // (ii) angles (:640-675)
     acc_init(a);
-    cc_angles(w, nb, nc, d0, nd, box, 0, 0.0, a);
-    a = block_reduce(a, sh_acc);
+    cc_angles(w, nb, nc, d0, nd, box, 0, 0.0, a, g);
+    a = group_reduce(a, gsh, g);
     const long long acnt = a.l[0], n_more = a.l[1], n_less = a.l[2], n_eq = a.l[3];
     if (acnt == 0) continue;                               // :674-675
     const double amean = a.s[0] / (double)acnt, amax = a.mx, amin = a.mn;
 
     // (iii) squared deviations of the angles and of the distance attribute (np.std: two-pass, population)
     acc_init(a);
-    cc_angles(w, nb, nc, d0, nd, box, 1, amean, a);
-    for (int j = tid; j < m; j += bd) {
+    cc_angles(w, nb, nc, d0, nd, box, 1, amean, a, g);
+    for (int j = g.lane; j < m; j += g.size) {
       const int ja = w.ea[e0 + j], jb = w.eb[e0 + j];
       if (ja != jb && inside(w, nb, ja, box) && inside(w, nb, jb, box)) {
         const double d = in.e_attr[(int64_t)w.esort[e0 + j] * in.A + acol] - dmean;
         a.s[1] += d * d;
       }
     }
-    a = block_reduce(a, sh_acc);
+    a = group_reduce(a, gsh, g);
     const double avar = a.s[0] / (double)acnt, dvar = a.s[1] / (double)mk;
 
-    if (tid == 0) {
-      const int nk = w.ccnt[slot];
+    if (g.lane == 0) {
       w.csurv[slot] = 1;
       w.cm[slot] = (int)mk;
       w.cms[slot] = (int)msk;
@@ -757,18 +821,39 @@ __global__ void __launch_bounds__(kThreads) k_prop_cc_main(In in, Ws w, int wmax
       w.clabel[slot] = hit ? (int)in.gt_labels[gsel] : in.n_classes - 1;
       w.chas[slot] = sel.ios > 0.7 ? 1 : 0;
       double* st = w.cstats + kStats * slot;
-      st[0] = (double)nk; st[1] = (double)mk; st[2] = (double)n_eq; st[3] = (double)n_less; st[4] = (double)n_more;
-      st[5] = width; st[6] = height; st[7] = amean; st[8] = amax; st[9] = amin; st[10] = sqrt(avar);
-      st[11] = dmean; st[12] = sqrt(dvar);
-      const double area = width * height;                  // :726-728: first maximum of the box area is the root
-      if (root < 0 || area > root_area) { root = (int)tb; root_area = area; }
-      tn += nk; te += mk; ts += msk; tb += 1;
+      st[0] = (double)w.ccnt[slot]; st[1] = (double)mk; st[2] = (double)n_eq; st[3] = (double)n_less;
+      st[4] = (double)n_more; st[5] = width; st[6] = height; st[7] = amean; st[8] = amax; st[9] = amin;
+      st[10] = sqrt(avar); st[11] = dmean; st[12] = sqrt(dvar);
     }
   }
+  __syncthreads();
+
+  // -- the component's survivors in candidate order: offsets inside the component's block, totals, and the root =
+  //    first maximum of the box area (:726-728)
+  I4 carry = i4_zero();
+  Acc best;
+  acc_init(best);
+  for (int base = 0; base < ncand; base += bd) {
+    const int k = base + tid;
+    I4 mine = i4_zero();
+    if (k < ncand && w.csurv[slot0 + k]) {
+      const int64_t slot = slot0 + k;
+      mine.v[0] = w.ccnt[slot]; mine.v[1] = w.cm[slot]; mine.v[2] = w.cms[slot]; mine.v[3] = 1;
+      const int32_t* q = w.cbox + 4 * slot;
+      const double area = (xv[q[2]] - xv[q[0]]) * (yv[q[3]] - yv[q[1]]);
+      if (area > best.key) { best.key = area; best.arg = k; }   // k ascends per thread: keeps the first maximum
+    }
+    I4 tot;
+    const I4 ex = block_excl_scan_i4(mine, sh_i4, &tot);
+    if (k < ncand)
+      for (int t = 0; t < 4; ++t) w.coff[4 * (slot0 + k) + t] = carry.v[t] + ex.v[t];
+    for (int t = 0; t < 4; ++t) carry.v[t] += tot.v[t];
+  }
+  best = block_reduce(best, sh_acc);                       // (its barriers also publish coff)
   if (tid == 0) {
-    w.cc_tot[4 * c] = tn; w.cc_tot[4 * c + 1] = te; w.cc_tot[4 * c + 2] = ts; w.cc_tot[4 * c + 3] = tb;
-    w.cc_root[c] = root;
-    if (tb == 0) raise_err(w.totals, YOLAT_PROP_ERR_NO_PROPOSAL, c);   // np.argmax of an empty area list raises (:728)
+    for (int t = 0; t < 4; ++t) w.cc_tot[4 * c + t] = carry.v[t];
+    w.cc_root[c] = carry.v[3] > 0 ? w.coff[4 * (slot0 + best.arg) + 3] : -1;   // ordinal of the root among the survivors
+    if (carry.v[3] == 0) raise_err(w.totals, YOLAT_PROP_ERR_NO_PROPOSAL, c);   // np.argmax of an empty area list raises (:728)
   }
 }
 
@@ -793,22 +878,21 @@ __global__ void __launch_bounds__(kThreads) k_prop_cc_scan(In in, Ws w) {
 // ---- (4b) one CTA per component writes its proposals (graph_dict3.py:598-603, :693-722) ---------------------------
 __device__ void fill_edges(const Ws& w, int64_t nb, const Box& box, int m, const int32_t* sorted, const int32_t* la,
                            const int32_t* lb, const double* attr_in, int A, int64_t node_off, int64_t edge_off,
-                           int64_t* edge_out, double* attr_out, int* sh) {
-  const int tid = threadIdx.x, bd = blockDim.x;
+                           const int32_t* lrank, int64_t* edge_out, double* attr_out, int* sh, const Group& g) {
   int done = 0;
-  for (int base = 0; base < m; base += bd) {
-    const int j = base + tid;
+  for (int base = 0; base < m; base += g.size) {
+    const int j = base + g.lane;
     int keep = 0, a = 0, b = 0;
     if (j < m) {
       a = la[j]; b = lb[j];
       keep = (a != b && inside(w, nb, a, box) && inside(w, nb, b, box)) ? 1 : 0;
     }
     int tot;
-    const int ex = block_excl_scan<int>(keep, sh, &tot);
+    const int ex = group_excl_scan(keep, sh, g, &tot);
     if (keep) {
       const int64_t o = edge_off + done + ex;
-      edge_out[2 * o] = node_off + w.lrank[nb + a];
-      edge_out[2 * o + 1] = node_off + w.lrank[nb + b];
+      edge_out[2 * o] = node_off + lrank[a];
+      edge_out[2 * o + 1] = node_off + lrank[b];
       const double* src = attr_in + (int64_t)sorted[j] * A;
       double* dst = attr_out + o * A;
       for (int q = 0; q < A; ++q) dst[q] = src[q];
@@ -818,41 +902,47 @@ __device__ void fill_edges(const Ws& w, int64_t nb, const Box& box, int m, const
 }
 
 __global__ void __launch_bounds__(kThreads) k_prop_fill(In in, Ws w, Out out, int wmax) {
-  __shared__ int sh[kThreads];
-  const int c = blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
+  __shared__ int sh_all[kThreads];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const Group g = this_group();
+  int* sh = sh_all + g.id * g.size;
   const int64_t nb = in.cc_ptr[c];
   const int nc = (int)(in.cc_ptr[c + 1] - nb);
   const int e0 = w.eptr[c], m = w.eptr[c + 1] - e0;
   const int s0 = w.sptr[c], ms = w.sptr[c + 1] - s0;
   const int64_t slot0 = (int64_t)c * wmax;
   const int ncand = w.ncand[c];
-  int64_t node_off = w.cc_off[4 * c], edge_off = w.cc_off[4 * c + 1], sup_off = w.cc_off[4 * c + 2];
-  int64_t box_off = w.cc_off[4 * c + 3];
+  const int64_t cc_node = w.cc_off[4 * c], cc_edge = w.cc_off[4 * c + 1], cc_sup = w.cc_off[4 * c + 2];
+  const int64_t cc_box = w.cc_off[4 * c + 3];
   if (tid == 0) {
-    out.cc_table[3 * c] = box_off;                         // first proposal of the component
+    out.cc_table[3 * c] = cc_box;                          // first proposal of the component
     out.cc_table[3 * c + 1] = w.cc_tot[4 * c + 3];         // how many
-    out.cc_table[3 * c + 2] = box_off + (w.cc_root[c] < 0 ? 0 : w.cc_root[c]);   // its root (largest box)
+    out.cc_table[3 * c + 2] = cc_box + (w.cc_root[c] < 0 ? 0 : w.cc_root[c]);   // its root (largest box)
     if (c == 0) { out.slice_pos[0] = 0; out.slice_edge[0] = 0; out.slice_super[0] = 0; out.slice_bbox[0] = 0; }
   }
   const double* xv = w.xv + nb;
   const double* yv = w.yv + nb;
-  for (int k = 0; k < ncand; ++k) {
+  int32_t* lrank = w.lrank + (int64_t)g.id * in.cc_total + nb;      // the group's own copy
+  for (int k = g.id; k < ncand; k += g.count) {              // one group per surviving candidate
     const int64_t slot = slot0 + k;
     if (!w.csurv[slot]) continue;
     const int32_t* q = w.cbox + 4 * slot;
     const Box box = {q[0], q[1], q[2], q[3]};
     const double pb[4] = {xv[box.x0], yv[box.y0], xv[box.x1], yv[box.y1]};
     const double width = pb[2] - pb[0], height = pb[3] - pb[1];
+    const int32_t* co = w.coff + 4 * slot;
+    const int64_t node_off = cc_node + co[0], edge_off = cc_edge + co[1], sup_off = cc_sup + co[2];
+    const int64_t box_off = cc_box + co[3];
     // nodes in ascending id order (the sorted tuple of :555), rank inside the proposal = the local o2n of :579-581
     int done = 0;
-    for (int base = 0; base < nc; base += bd) {
-      const int r = base + tid;
+    for (int base = 0; base < nc; base += g.size) {
+      const int r = base + g.lane;
       const int keep = (r < nc && inside(w, nb, r, box)) ? 1 : 0;
       int tot;
-      const int ex = block_excl_scan<int>(keep, sh, &tot);
+      const int ex = group_excl_scan(keep, sh, g, &tot);
       if (keep) {
         const int lr = done + ex;
-        w.lrank[nb + r] = lr;
+        lrank[r] = lr;
         const int v = w.cs[nb + r];
         const int64_t o = node_off + lr;
         double px = w.pos[2 * v], py = w.pos[2 * v + 1];
@@ -867,18 +957,18 @@ __global__ void __launch_bounds__(kThreads) k_prop_fill(In in, Ws w, Out out, in
       }
       done += tot;
     }
-    __syncthreads();                                       // lrank visible to the edge writers
-    fill_edges(w, nb, box, m, w.esort + e0, w.ea + e0, w.eb + e0, in.e_attr, in.A, node_off, edge_off, out.edge,
-               out.e_attr, sh);
-    fill_edges(w, nb, box, ms, w.ssort + s0, w.sa + s0, w.sb + s0, in.e_attr_super, in.As, node_off, sup_off,
-               out.edge_super, out.e_attr_super, sh);
-    if (tid == 0) {
-      const int g = w.cgt[slot];
+    __syncwarp();                                          // lrank visible to the group's edge writers
+    fill_edges(w, nb, box, m, w.esort + e0, w.ea + e0, w.eb + e0, in.e_attr, in.A, node_off, edge_off, lrank, out.edge,
+               out.e_attr, sh, g);
+    fill_edges(w, nb, box, ms, w.ssort + s0, w.sa + s0, w.sb + s0, in.e_attr_super, in.As, node_off, sup_off, lrank,
+               out.edge_super, out.e_attr_super, sh, g);
+    if (g.lane == 0) {
+      const int gt = w.cgt[slot];
       out.labels[box_off] = w.clabel[slot];
       out.has_obj[box_off] = w.chas[slot];
       for (int t = 0; t < 4; ++t) {
         out.bbox[4 * box_off + t] = pb[t];
-        out.bbox_targets[4 * box_off + t] = g >= 0 ? in.gt_bbox[4 * (int64_t)g + t] : 0.0;
+        out.bbox_targets[4 * box_off + t] = gt >= 0 ? in.gt_bbox[4 * (int64_t)gt + t] : 0.0;
       }
       for (int t = 0; t < kStats; ++t) out.stat_feats[kStats * box_off + t] = w.cstats[kStats * slot + t];
       out.slice_pos[box_off + 1] = node_off + w.ccnt[slot];
@@ -886,11 +976,7 @@ __global__ void __launch_bounds__(kThreads) k_prop_fill(In in, Ws w, Out out, in
       out.slice_super[box_off + 1] = sup_off + w.cms[slot];
       out.slice_bbox[box_off + 1] = box_off + 1;
     }
-    node_off += w.ccnt[slot];
-    edge_off += w.cm[slot];
-    sup_off += w.cms[slot];
-    box_off += 1;
-    __syncthreads();                                       // lrank is rewritten by the next proposal
+    __syncwarp();                                          // lrank is rewritten by the group's next proposal
   }
 }
 
