@@ -266,6 +266,31 @@ def test_enumerator_has_no_cpu_path():
         P.ProposalEnumerator(17, do_mixup=True)._get_proposal(gd, gt, gl, bbox_sampling_step=5)
 
 
+@pytest.mark.skipif(not os.path.isdir('/root/reference/Datasets'), reason='reference tree not on this machine')
+def test_overlay_binds_to_the_reference_dataset_class(monkeypatch):
+    """the one-line overlay on the UNMODIFIED `SESYDFloorPlan` routes its `_get_proposal` call
+    (graph_dict3.py:929) here -- reading n_classes / normalize_bbox / do_mixup from the Dataset instance."""
+    import torch
+    from oracle import make_golden_proposals as MG
+    cls = MG.reference_class()
+    monkeypatch.setattr(cls, '_get_proposal', P.ProposalEnumerator._get_proposal)
+    ds = cls.__new__(cls)
+    ds.n_classes, ds.normalize_bbox, ds.do_mixup = 17, True, True
+    gd, gt, gl = _tiny()
+    with pytest.raises(NotImplementedError):                   # mixup is random augmentation, not on this path
+        ds._get_proposal(gd, gt, gl, bbox_sampling_step=5)
+    ds.do_mixup = False
+    seen = {}
+    monkeypatch.setattr(P, 'get_proposal', lambda *a: seen.setdefault('args', a) and None)
+    ds._get_proposal(gd, gt, gl, bbox_sampling_step=5)
+    assert seen['args'][3:] == (5, 17, True) and seen['args'][0] is gd
+    monkeypatch.undo()
+    if not torch.cuda.is_available():
+        monkeypatch.setattr(cls, '_get_proposal', P.ProposalEnumerator._get_proposal)
+        with pytest.raises(Exception, match='CPU|missing'):    # no silent fallback to the python loops
+            ds._get_proposal(gd, gt, gl, bbox_sampling_step=5)
+
+
 # ---------------------------------------------------------------- the real kernels
 @pytest.mark.gpu
 def test_gpu_proposals_match_goldens_and_oracle():
