@@ -265,6 +265,7 @@ def canonical_order(result):
         for m in members:
             values[m.value['idx_bbox']] = m.value
         ids = sorted((m.value['idx_bbox'] for m in members), key=lambda i: tuple(bbox[i].tolist()))
+        assert len({tuple(bbox[i].tolist()) for i in ids}) == len(ids), 'two proposals of one component share a box'
         root_of.append(len(order) + ids.index(root.value['idx_bbox']))
         order += ids
     assert sorted(order) == list(range(b)), 'roots do not cover every proposal exactly once'
